@@ -1,0 +1,204 @@
+"""ctypes binding of include/escort_b200.h.  Device buffers are torch CUDA tensors; every call goes through
+the C ABI exactly as the Caffe overlay would.  No fallback: a missing library raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libescort_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError("caffe_escoin_b200: %s is missing -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+                      "(there is no CPU or PyTorch fallback for the sparse-conv path)" % LIB_PATH)
+
+lib = C.CDLL(LIB_PATH)
+
+
+class Geom(C.Structure):
+    """escort_geom (BaseConvolutionLayer member names)."""
+    _fields_ = [(n, C.c_int) for n in ("channels", "num_output", "group", "height", "width", "kernel_h", "kernel_w",
+                                       "pad_h", "pad_w", "stride_h", "stride_w", "dilation_h", "dilation_w")]
+
+
+EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
+           "escort_plan_destroy", "escort_plan_nnz", "escort_plan_kernel_name", "escort_plan_set_variant",
+           "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
+           "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_measure_fp32_peak",
+           "escort_last_error", "escort_version"]
+
+lib.escort_last_error.restype = C.c_char_p
+lib.escort_version.restype = C.c_char_p
+lib.escort_plan_kernel_name.restype = C.c_char_p
+lib.escort_plan_kernel_name.argtypes = [C.c_void_p]
+lib.escort_plan_nnz.restype = C.c_long
+lib.escort_plan_nnz.argtypes = [C.c_void_p]
+lib.escort_plan_destroy.argtypes = [C.c_void_p]
+lib.escort_plan_set_variant.argtypes = [C.c_void_p, C.c_int]
+
+
+class EscortError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise EscortError("%s failed (rc=%d): %s" % (what, rc, lib.escort_last_error().decode()))
+
+
+def _ptr(t):
+    if t is None:
+        return C.c_void_p(0)
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor required"
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream(stream):
+    if stream is None:
+        stream = torch.cuda.current_stream()
+    return C.c_void_p(stream.cuda_stream)
+
+
+def out_dim(i, pad, k, s, d=1):
+    return (i + 2 * pad - (d * (k - 1) + 1)) // s + 1
+
+
+def make_geom(Cin, Cout, H, W, k, stride=1, pad=0, dilation=1, group=1, kw=None, pad_w=None, stride_w=None,
+              dilation_w=None):
+    return Geom(Cin, Cout, group, H, W, k, k if kw is None else kw, pad, pad if pad_w is None else pad_w, stride,
+                stride if stride_w is None else stride_w, dilation, dilation if dilation_w is None else dilation_w)
+
+
+def pack_csr(A2d, stream=None, want_nnz_per_row=True):
+    """escort_pack_csr on a row-major M x N device matrix. Returns (values, colidx, rowptr, nnz_per_row, nnz)."""
+    M, N = A2d.shape
+    dev = A2d.device
+    values = torch.zeros(M * N, dtype=torch.float32, device=dev)
+    colidx = torch.zeros(M * N, dtype=torch.int32, device=dev)
+    rowptr = torch.zeros(M + 1, dtype=torch.int32, device=dev)
+    npr = torch.zeros(M, dtype=torch.int32, device=dev) if want_nnz_per_row else None
+    nnz = C.c_int(-1)
+    _check(lib.escort_pack_csr(M, N, _ptr(A2d), _ptr(npr), _ptr(values), _ptr(rowptr), _ptr(colidx), C.byref(nnz),
+                               _stream(stream)), "escort_pack_csr")
+    return values, colidx, rowptr, npr, nnz.value
+
+
+def weight_align(weights, geom, stretch=True, stream=None):
+    """BaseConvolutionLayer::WeightAlign, GPU branch (reference base_conv_layer.cpp:236-264): per group
+    dense->CSR into the layer's worst-case-sized blobs, then stretch.  Returns dict like the oracle's."""
+    g = geom
+    M = g.num_output // g.group
+    N = (g.channels // g.group) * g.kernel_h * g.kernel_w
+    dev = weights.device
+    w = weights.contiguous().view(g.num_output, N)
+    values = torch.zeros(g.num_output * N, dtype=torch.float32, device=dev)
+    colidx = torch.zeros(g.num_output * N, dtype=torch.int32, device=dev)
+    rowptr = torch.zeros(g.num_output + g.group, dtype=torch.int32, device=dev)
+    npr = torch.zeros(g.num_output, dtype=torch.int32, device=dev)
+    nz_num = []
+    woff, roff = M * N, M + 1
+    for gi in range(g.group):
+        nnz = C.c_int(-1)
+        _check(lib.escort_pack_csr(M, N, C.c_void_p(w.data_ptr() + 4 * woff * gi),
+                                   C.c_void_p(npr.data_ptr() + 4 * M * gi),
+                                   C.c_void_p(values.data_ptr() + 4 * woff * gi),
+                                   C.c_void_p(rowptr.data_ptr() + 4 * roff * gi),
+                                   C.c_void_p(colidx.data_ptr() + 4 * woff * gi), C.byref(nnz), _stream(stream)),
+               "escort_pack_csr")
+        nz_num.append(nnz.value)
+        if stretch:
+            _check(lib.escort_stretch(C.c_void_p(rowptr.data_ptr() + 4 * roff * gi),
+                                      C.c_void_p(colidx.data_ptr() + 4 * woff * gi), M, g.height, g.width, g.pad_h,
+                                      g.pad_w, g.kernel_h, g.kernel_w, _stream(stream)), "escort_stretch")
+    return dict(values=values, colidx=colidx, rowptr=rowptr, nnz_per_row=npr, nz_num=nz_num, stretched=stretch)
+
+
+class Plan:
+    """Owner of an escort_plan*."""
+
+    def __init__(self, geom, csr, stream=None):
+        self.geom = geom
+        self.Ho = out_dim(geom.height, geom.pad_h, geom.kernel_h, geom.stride_h, geom.dilation_h)
+        self.Wo = out_dim(geom.width, geom.pad_w, geom.kernel_w, geom.stride_w, geom.dilation_w)
+        h = C.c_void_p(0)
+        _check(lib.escort_plan_create(C.byref(geom), _ptr(csr["rowptr"]), _ptr(csr["colidx"]), _ptr(csr["values"]),
+                                      int(bool(csr.get("stretched", True))), C.byref(h), _stream(stream)),
+               "escort_plan_create")
+        self.h = h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib.escort_plan_destroy(self.h)
+            self.h = None
+
+    @property
+    def nnz(self):
+        return lib.escort_plan_nnz(self.h)
+
+    @property
+    def kernel_name(self):
+        return lib.escort_plan_kernel_name(self.h).decode()
+
+    def set_variant(self, v):
+        _check(lib.escort_plan_set_variant(self.h, int(v)), "escort_plan_set_variant")
+
+    def forward(self, bottom, bias=None, relu=False, top=None, stream=None):
+        g = self.geom
+        num = bottom.shape[0]
+        if top is None:
+            top = torch.empty((num, g.num_output, self.Ho, self.Wo), dtype=torch.float32, device=bottom.device)
+        _check(lib.escort_sconv_forward(self.h, num, _ptr(bottom), _ptr(bias), int(relu), _ptr(top), _stream(stream)),
+               "escort_sconv_forward")
+        return top
+
+    def backward_data(self, top_diff, bottom_diff=None, stream=None):
+        g = self.geom
+        num = top_diff.shape[0]
+        if bottom_diff is None:
+            bottom_diff = torch.empty((num, g.channels, g.height, g.width), dtype=torch.float32,
+                                      device=top_diff.device)
+        _check(lib.escort_sconv_backward_data(self.h, num, _ptr(top_diff), _ptr(bottom_diff), _stream(stream)),
+               "escort_sconv_backward_data")
+        return bottom_diff
+
+    def backward_weight(self, bottom, top_diff, wd_dense=None, wd_csr=None, accumulate=True, stream=None):
+        _check(lib.escort_sconv_backward_weight(self.h, bottom.shape[0], _ptr(bottom), _ptr(top_diff), _ptr(wd_dense),
+                                                _ptr(wd_csr), int(accumulate), _stream(stream)),
+               "escort_sconv_backward_weight")
+
+    def refresh_values(self, weights_dense, values_csr=None, stream=None):
+        _check(lib.escort_refresh_values(self.h, _ptr(weights_dense), _ptr(values_csr), _stream(stream)),
+               "escort_refresh_values")
+
+
+def bias_backward(top_diff, bias_diff, stream=None):
+    num, M = top_diff.shape[0], top_diff.shape[1]
+    spatial = top_diff.shape[2] * top_diff.shape[3]
+    _check(lib.escort_bias_backward(num, M, spatial, _ptr(top_diff), _ptr(bias_diff), _stream(stream)),
+           "escort_bias_backward")
+
+
+def copy_input(dst, src, Cn, H, W, pad_h, pad_w, stream=None):
+    _check(lib.escort_copy_input(_ptr(dst), _ptr(src), Cn, H, W, pad_h, pad_w, _stream(stream)), "escort_copy_input")
+
+
+def sconv_padded(fuse_relu, num, inp, ifmap_size, rowptr, colidx, values, bias, H, W, pad_h, pad_w, stride_h,
+                 stride_w, dil_h, dil_w, kh, kw, out, num_oc, num_groups, stream=None):
+    """caffe_gpu_sconv's exact argument list (pointers may be ints = device addresses)."""
+    def p(x):
+        return C.c_void_p(x) if isinstance(x, int) else _ptr(x)
+    _check(lib.escort_sconv_padded(int(fuse_relu), num, p(inp), ifmap_size, p(rowptr), p(colidx), p(values), p(bias),
+                                   H, W, pad_h, pad_w, stride_h, stride_w, dil_h, dil_w, kh, kw, p(out), num_oc,
+                                   num_groups, _stream(stream)), "escort_sconv_padded")
+
+
+def allreduce_grads(flat, scale, comm=None, stream=None):
+    _check(lib.escort_allreduce_grads(C.c_void_p(comm or 0), _ptr(flat), C.c_size_t(flat.numel()), C.c_float(scale),
+                                      _stream(stream)), "escort_allreduce_grads")
+
+
+def measure_fp32_peak(variant=0, iters=4096):
+    tf, sms, khz = C.c_double(0), C.c_int(0), C.c_int(0)
+    _check(lib.escort_measure_fp32_peak(variant, iters, C.byref(tf), C.byref(sms), C.byref(khz)),
+           "escort_measure_fp32_peak")
+    return tf.value, sms.value, khz.value

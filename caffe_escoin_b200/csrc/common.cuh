@@ -1,0 +1,80 @@
+// common.cuh -- shared declarations of the escort_b200 library (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "escort_b200.h"
+
+namespace escort {
+
+void set_last_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+
+#define ESCORT_CUDA(call)                                                          \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) return ::escort::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define ESCORT_LAUNCH_CHECK() ESCORT_CUDA(cudaGetLastError())
+
+#define ESCORT_REQUIRE(cond, msg)                 \
+  do {                                            \
+    if (!(cond)) {                                \
+      ::escort::set_last_error(std::string(msg)); \
+      return ESCORT_EINVAL;                       \
+    }                                             \
+  } while (0)
+
+inline int out_dim(int in, int pad, int k, int s, int d) { return (in + 2 * pad - (d * (k - 1) + 1)) / s + 1; }
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// One nonzero in layer-global coordinates (all groups flattened), host side.
+struct Nz {
+  int oc;        // global output channel
+  int ic;        // global input channel
+  int kh, kw;
+  float val;
+  int csr_pos;   // position in the reference's blob layout (weight_offset*g + j)
+  int dense_idx; // index into the dense M x C/g x kh x kw weight tensor
+};
+
+struct TilePlan;  // sconv_tile.cu
+
+}  // namespace escort
+
+// The opaque plan (declared in escort_b200.h).
+struct escort_plan {
+  escort_geom g;
+  int Ho, Wo;
+  int device;
+  long nnz;
+  int variant;  // -1 auto
+  // ---- generic forward: row-major (global rows) ----
+  int *d_rowptr;    // num_output + 1
+  int4 *d_meta;     // nnz: {in_off, dy, dx, val bits}; in_off = ic*H*W + dy*W + dx  (may be negative)
+  // ---- bookkeeping for refresh / gradient scatter ----
+  int *d_dense_idx; // nnz (row-major order) -> dense weight index
+  int *d_csr_pos;   // nnz (row-major order) -> position in reference CSR blob layout
+  // ---- backward data: grouped by input channel ----
+  int *d_colptr;    // channels + 1
+  int4 *d_tmeta;    // nnz: {oc, dy, dx, val bits}
+  int *d_tsrc;      // nnz: transposed slot -> row-major nonzero index
+  // ---- backward weight ----
+  int4 *d_wmeta;    // nnz (row-major order): {oc, ic, dy, dx}
+  // ---- tile-interpreter forward (sconv_tile.cu) ----
+  escort::TilePlan *tile;
+  std::vector<escort::Nz> *host_nz;  // kept for re-planning with another variant
+};
+
+namespace escort {
+// sconv_tile.cu
+int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream);
+void tile_plan_free(TilePlan *tp);
+int tile_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,
+                 cudaStream_t stream);
+int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream);
+const char *tile_kernel_name(const TilePlan *tp);
+}  // namespace escort

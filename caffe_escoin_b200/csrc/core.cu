@@ -1,0 +1,538 @@
+// core.cu -- plan construction, the reference-ABI compatibility kernel, and the generic (any geometry)
+// forward / masked-backward kernels of the Escort direct sparse convolution.
+//
+// The generic kernels are the always-correct CUDA path for every stride / pad / dilation / group
+// combination; the register-blocked tile interpreter in sconv_tile.cu is selected by the plan when the
+// geometry fits it.  There is no CPU path.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace escort {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "%s failed: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  g_last_error = buf;
+  return (int)e;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// a6 (compat): the reference's caffe_gpu_sconv contract -- padded input, stretched colidx.
+// One CTA = 128 consecutive output pixels of one (image, out-channel); the CSR row is streamed through
+// shared memory in chunks so (colidx, value) are fetched once per CTA (the reference's sconv_shm idea,
+// math_functions.cu:264-319), and the whole batch is one launch.
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kCompatThreads = 128;
+static constexpr int kCompatChunk = 512;
+
+template <bool DILATED>
+__global__ void __launch_bounds__(kCompatThreads)
+    sconv_padded_kernel(const int *__restrict__ rowptr, const int *__restrict__ colidx,
+                        const float *__restrict__ values, const float *__restrict__ input, long in_img_stride,
+                        const float *__restrict__ bias, int fuse_relu, float *__restrict__ output,
+                        long out_img_stride, int num_oc, int Hp, int Wp, int stride_h, int stride_w, int dil_h,
+                        int dil_w, int Ho, int Wo) {
+  __shared__ int col_s[kCompatChunk];
+  __shared__ float val_s[kCompatChunk];
+  const int oc = blockIdx.y;
+  const int n = blockIdx.z;
+  const int pix = blockIdx.x * kCompatThreads + threadIdx.x;
+  const bool active = pix < Ho * Wo;
+  const int oy = active ? pix / Wo : 0, ox = active ? pix % Wo : 0;
+  const float *in = input + (long)n * in_img_stride;
+  const float *in_ptr = in + (long)oy * stride_h * Wp + ox * stride_w;
+  const int row_start = rowptr[oc], row_end = rowptr[oc + 1];
+  float sum = (fuse_relu && bias) ? bias[oc] : 0.f;
+  for (int base = row_start; base < row_end; base += kCompatChunk) {
+    const int len = min(kCompatChunk, row_end - base);
+    for (int i = threadIdx.x; i < len; i += kCompatThreads) {
+      col_s[i] = __ldg(colidx + base + i);
+      val_s[i] = __ldg(values + base + i);
+    }
+    __syncthreads();
+    if (active) {
+      if (!DILATED) {
+        for (int i = 0; i < len; ++i) sum = fmaf(val_s[i], __ldg(in_ptr + col_s[i]), sum);
+      } else {
+        for (int i = 0; i < len; ++i) {
+          const int off = col_s[i];
+          const int kc = off % Wp, kr = (off / Wp) % Hp, ic = off / (Wp * Hp);
+          const int iy = kr * dil_h + oy * stride_h, ix = kc * dil_w + ox * stride_w;
+          sum = fmaf(val_s[i], __ldg(in + ((long)ic * Hp + iy) * Wp + ix), sum);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    if (fuse_relu) sum = fmaxf(sum, 0.f);
+    output[(long)n * out_img_stride + (long)oc * Ho * Wo + pix] = sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic forward from the UNPADDED tensor: halo handled by predication, bias/ReLU fused.
+// meta[j] = {in_off, dy, dx, value}: input element = x[n][...][(oy*sh + dy), (ox*sw + dx)] with
+// in_off = ic*H*W + dy*W + dx (so address = base(oy*sh, ox*sw) + in_off).
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kGenThreads = 128;
+static constexpr int kGenChunk = 256;
+
+__global__ void __launch_bounds__(kGenThreads)
+    sconv_fwd_generic_kernel(const int *__restrict__ rowptr, const int4 *__restrict__ meta,
+                             const float *__restrict__ bottom, const float *__restrict__ bias, int fuse_relu,
+                             float *__restrict__ top, int C, int H, int W, int M, int Ho, int Wo, int stride_h,
+                             int stride_w) {
+  __shared__ int4 meta_s[kGenChunk];
+  const int oc = blockIdx.y, n = blockIdx.z;
+  const int pix = blockIdx.x * kGenThreads + threadIdx.x;
+  const bool active = pix < Ho * Wo;
+  const int oy = active ? pix / Wo : 0, ox = active ? pix % Wo : 0;
+  const int iy0 = oy * stride_h, ix0 = ox * stride_w;
+  const float *in = bottom + (long)n * C * H * W + (long)iy0 * W + ix0;
+  const int row_start = rowptr[oc], row_end = rowptr[oc + 1];
+  float sum = bias ? bias[oc] : 0.f;
+  for (int base = row_start; base < row_end; base += kGenChunk) {
+    const int len = min(kGenChunk, row_end - base);
+    for (int i = threadIdx.x; i < len; i += kGenThreads) meta_s[i] = __ldg(meta + base + i);
+    __syncthreads();
+    if (active) {
+      for (int i = 0; i < len; ++i) {
+        const int4 m = meta_s[i];
+        const int iy = iy0 + m.y, ix = ix0 + m.z;
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+          sum = fmaf(__int_as_float(m.w), __ldg(in + m.x), sum);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+    if (fuse_relu) sum = fmaxf(sum, 0.f);
+    top[((long)n * M + oc) * Ho * Wo + pix] = sum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic backward-data: bottom_diff[n][c][iy][ix] = sum over nonzeros (oc,c,kh,kw) of
+//   w * top_diff[n][oc][(iy - dy)/sh][(ix - dx)/sw]   when divisible and in range.  Overwrites.
+// tmeta (grouped by input channel c) = {oc, dy, dx, value}.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGenThreads)
+    sconv_bwd_data_generic_kernel(const int *__restrict__ colptr, const int4 *__restrict__ tmeta,
+                                  const float *__restrict__ top_diff, float *__restrict__ bottom_diff, int C, int H,
+                                  int W, int M, int Ho, int Wo, int stride_h, int stride_w) {
+  __shared__ int4 meta_s[kGenChunk];
+  const int c = blockIdx.y, n = blockIdx.z;
+  const int pix = blockIdx.x * kGenThreads + threadIdx.x;
+  const bool active = pix < H * W;
+  const int iy = active ? pix / W : 0, ix = active ? pix % W : 0;
+  const float *td = top_diff + (long)n * M * Ho * Wo;
+  const int start = colptr[c], end = colptr[c + 1];
+  float sum = 0.f;
+  for (int base = start; base < end; base += kGenChunk) {
+    const int len = min(kGenChunk, end - base);
+    for (int i = threadIdx.x; i < len; i += kGenThreads) meta_s[i] = __ldg(tmeta + base + i);
+    __syncthreads();
+    if (active) {
+      for (int i = 0; i < len; ++i) {
+        const int4 m = meta_s[i];
+        const int ty = iy - m.y, tx = ix - m.z;
+        if (ty < 0 || tx < 0) continue;
+        int oy = ty, ox = tx;
+        if (stride_h != 1) {
+          if (ty % stride_h) continue;
+          oy = ty / stride_h;
+        }
+        if (stride_w != 1) {
+          if (tx % stride_w) continue;
+          ox = tx / stride_w;
+        }
+        if (oy < Ho && ox < Wo) sum = fmaf(__int_as_float(m.w), __ldg(td + ((long)m.x * Ho + oy) * Wo + ox), sum);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) bottom_diff[((long)n * C + c) * H * W + pix] = sum;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// generic backward-weight, restricted to the mask: one warp per nonzero,
+//   g = sum_{n,oy,ox} top_diff[n][oc][oy][ox] * bottom[n][ic][oy*sh+dy][ox*sw+dx].
+// wmeta (row-major order) = {oc, ic, dy, dx}.
+// ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    sconv_bwd_weight_generic_kernel(long nnz, const int4 *__restrict__ wmeta, const int *__restrict__ dense_idx,
+                                    const int *__restrict__ csr_pos, const float *__restrict__ bottom,
+                                    const float *__restrict__ top_diff, int num, int C, int H, int W, int M, int Ho,
+                                    int Wo, int stride_h, int stride_w, float *__restrict__ wd_dense,
+                                    float *__restrict__ wd_csr, int accumulate) {
+  const long j = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (j >= nnz) return;
+  const int4 m = __ldg(wmeta + j);
+  const int oc = m.x, ic = m.y, dy = m.z, dx = m.w;
+  // valid output range so that the input coordinate is inside the image
+  int oy_lo = 0, oy_hi = Ho, ox_lo = 0, ox_hi = Wo;
+  while (oy_lo < Ho && oy_lo * stride_h + dy < 0) ++oy_lo;
+  while (oy_hi > oy_lo && (oy_hi - 1) * stride_h + dy >= H) --oy_hi;
+  while (ox_lo < Wo && ox_lo * stride_w + dx < 0) ++ox_lo;
+  while (ox_hi > ox_lo && (ox_hi - 1) * stride_w + dx >= W) --ox_hi;
+  const int ny = oy_hi - oy_lo, nx = ox_hi - ox_lo;
+  float sum = 0.f;
+  if (ny > 0 && nx > 0) {
+    const int per_img = ny * nx;
+    const long total = (long)num * per_img;
+    for (long t = lane; t < total; t += 32) {
+      const int n = (int)(t / per_img);
+      const int r = (int)(t % per_img);
+      const int oy = oy_lo + r / nx, ox = ox_lo + r % nx;
+      const float a = __ldg(top_diff + (((long)n * M + oc) * Ho + oy) * Wo + ox);
+      const float b = __ldg(bottom + (((long)n * C + ic) * H + oy * stride_h + dy) * W + ox * stride_w + dx);
+      sum = fmaf(a, b, sum);
+    }
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if (lane == 0) {
+    if (wd_dense) wd_dense[dense_idx[j]] += sum;
+    if (wd_csr) {
+      const int p = csr_pos[j];
+      wd_csr[p] = accumulate ? wd_csr[p] + sum : sum;
+    }
+  }
+}
+
+// bias_diff[oc] += sum_{n,pix} top_diff
+__global__ void __launch_bounds__(256) bias_backward_kernel(int num, int M, int spatial,
+                                                            const float *__restrict__ top_diff,
+                                                            float *__restrict__ bias_diff) {
+  __shared__ float part[8];
+  const int oc = blockIdx.x;
+  float sum = 0.f;
+  const long total = (long)num * spatial;
+  for (long t = threadIdx.x; t < total; t += blockDim.x) {
+    const int n = (int)(t / spatial);
+    const int p = (int)(t % spatial);
+    sum += __ldg(top_diff + ((long)n * M + oc) * spatial + p);
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += part[i];
+    bias_diff[oc] += s;
+  }
+}
+
+// values refresh: re-gather at fixed positions
+__global__ void refresh_kernel(long nnz, const float *__restrict__ w_dense, const int *__restrict__ dense_idx,
+                               const int *__restrict__ csr_pos, int4 *__restrict__ meta, float *__restrict__ values_csr) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= nnz) return;
+  const float v = __ldg(w_dense + dense_idx[j]);
+  meta[j].w = __float_as_int(v);
+  if (values_csr) values_csr[csr_pos[j]] = v;
+}
+__global__ void refresh_t_kernel(long nnz, const int4 *__restrict__ meta, const int *__restrict__ tsrc,
+                                 int4 *__restrict__ tmeta) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nnz) return;
+  tmeta[t].w = meta[tsrc[t]].w;
+}
+
+template <typename T>
+static int upload(T **dptr, const std::vector<T> &h, cudaStream_t stream) {
+  *dptr = nullptr;
+  const size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  ESCORT_CUDA(cudaMalloc((void **)dptr, bytes));
+  if (!h.empty()) ESCORT_CUDA(cudaMemcpyAsync(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+  return 0;
+}
+
+}  // namespace escort
+
+using namespace escort;
+
+extern "C" const char *escort_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char *escort_version(void) { return "escort_b200 0.1 (sm_100a)"; }
+
+extern "C" int escort_sconv_padded(int fuse_relu, int num, const float *input, int ifmap_size, const int *rowptr,
+                                   const int *colidx, const float *values, const float *bias, int height, int width,
+                                   int pad_h, int pad_w, int stride_h, int stride_w, int dilation_h, int dilation_w,
+                                   int kernel_h, int kernel_w, float *output, int num_oc, int num_groups,
+                                   escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(input && rowptr && colidx && values && output && num > 0 && num_oc > 0 && num_groups > 0,
+                 "escort_sconv_padded: bad arguments");
+  ESCORT_REQUIRE(!fuse_relu || bias, "escort_sconv_padded: fuse_relu requires bias (reference sconv_relu_*)");
+  const int Ho = out_dim(height, pad_h, kernel_h, stride_h, dilation_h);
+  const int Wo = out_dim(width, pad_w, kernel_w, stride_w, dilation_w);
+  ESCORT_REQUIRE(Ho > 0 && Wo > 0, "escort_sconv_padded: empty output");
+  dim3 grid(ceil_div(Ho * Wo, kCompatThreads), num_oc, num);
+  const long in_stride = (long)ifmap_size * num_groups;
+  const long out_stride = (long)num_oc * num_groups * Ho * Wo;
+  if (dilation_h != 1 || dilation_w != 1)
+    sconv_padded_kernel<true><<<grid, kCompatThreads, 0, stream>>>(
+        rowptr, colidx, values, input, in_stride, bias, fuse_relu, output, out_stride, num_oc, height + pad_h,
+        width + pad_w, stride_h, stride_w, dilation_h, dilation_w, Ho, Wo);
+  else
+    sconv_padded_kernel<false><<<grid, kCompatThreads, 0, stream>>>(
+        rowptr, colidx, values, input, in_stride, bias, fuse_relu, output, out_stride, num_oc, height + pad_h,
+        width + pad_w, stride_h, stride_w, 1, 1, Ho, Wo);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, const int *colidx, const float *values,
+                                  int colidx_is_stretched, escort_plan **plan_out, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(geom && rowptr && colidx && values && plan_out, "escort_plan_create: null argument");
+  const escort_geom g = *geom;
+  ESCORT_REQUIRE(g.channels > 0 && g.num_output > 0 && g.group > 0 && g.channels % g.group == 0 &&
+                     g.num_output % g.group == 0,
+                 "escort_plan_create: channels/num_output must be positive multiples of group");
+  ESCORT_REQUIRE(g.kernel_h > 0 && g.kernel_w > 0 && g.stride_h > 0 && g.stride_w > 0 && g.dilation_h > 0 &&
+                     g.dilation_w > 0 && g.pad_h >= 0 && g.pad_w >= 0 && g.height > 0 && g.width > 0,
+                 "escort_plan_create: bad geometry");
+  const int Ho = out_dim(g.height, g.pad_h, g.kernel_h, g.stride_h, g.dilation_h);
+  const int Wo = out_dim(g.width, g.pad_w, g.kernel_w, g.stride_w, g.dilation_w);
+  ESCORT_REQUIRE(Ho > 0 && Wo > 0, "escort_plan_create: empty output");
+  const int Mg = g.num_output / g.group, Cg = g.channels / g.group;
+  const long weight_offset = (long)Mg * Cg * g.kernel_h * g.kernel_w;
+  const int row_offset = Mg + 1;
+
+  // fetch the layer's CSR blobs
+  std::vector<int> h_rowptr((size_t)g.num_output + g.group);
+  ESCORT_CUDA(cudaMemcpyAsync(h_rowptr.data(), rowptr, h_rowptr.size() * sizeof(int), cudaMemcpyDeviceToHost, stream));
+  ESCORT_CUDA(cudaStreamSynchronize(stream));
+  std::vector<std::vector<int>> h_col(g.group);
+  std::vector<std::vector<float>> h_val(g.group);
+  long nnz = 0;
+  for (int gi = 0; gi < g.group; ++gi) {
+    const int *rp = h_rowptr.data() + (size_t)row_offset * gi;
+    ESCORT_REQUIRE(rp[0] == 0, "escort_plan_create: each group's rowptr must start at 0");
+    for (int i = 0; i < Mg; ++i) ESCORT_REQUIRE(rp[i + 1] >= rp[i], "escort_plan_create: rowptr not monotone");
+    const int n_g = rp[Mg];
+    ESCORT_REQUIRE(n_g <= weight_offset, "escort_plan_create: nnz exceeds dense size");
+    h_col[gi].resize(n_g);
+    h_val[gi].resize(n_g);
+    if (n_g) {
+      ESCORT_CUDA(cudaMemcpyAsync(h_col[gi].data(), colidx + weight_offset * gi, n_g * sizeof(int),
+                                  cudaMemcpyDeviceToHost, stream));
+      ESCORT_CUDA(cudaMemcpyAsync(h_val[gi].data(), values + weight_offset * gi, n_g * sizeof(float),
+                                  cudaMemcpyDeviceToHost, stream));
+    }
+    nnz += n_g;
+  }
+  ESCORT_CUDA(cudaStreamSynchronize(stream));
+
+  auto *nzs = new std::vector<Nz>();
+  nzs->reserve(nnz);
+  std::vector<int> g_rowptr(g.num_output + 1, 0);
+  const int Hp = g.height + g.pad_h, Wp = g.width + g.pad_w;
+  for (int gi = 0; gi < g.group; ++gi) {
+    const int *rp = h_rowptr.data() + (size_t)row_offset * gi;
+    for (int i = 0; i < Mg; ++i) {
+      for (int j = rp[i]; j < rp[i + 1]; ++j) {
+        const int col = h_col[gi][j];
+        int ic, kh, kw;
+        if (colidx_is_stretched) {
+          kw = col % Wp;
+          kh = (col / Wp) % Hp;
+          ic = col / (Wp * Hp);
+        } else {
+          kw = col % g.kernel_w;
+          kh = (col / g.kernel_w) % g.kernel_h;
+          ic = col / (g.kernel_w * g.kernel_h);
+        }
+        if (ic < 0 || ic >= Cg || kh >= g.kernel_h || kw >= g.kernel_w || col < 0) {
+          delete nzs;
+          set_last_error("escort_plan_create: column index out of range (wrong colidx_is_stretched?)");
+          return ESCORT_EINVAL;
+        }
+        Nz z;
+        z.oc = gi * Mg + i;
+        z.ic = gi * Cg + ic;
+        z.kh = kh;
+        z.kw = kw;
+        z.val = h_val[gi][j];
+        z.csr_pos = (int)(weight_offset * gi + j);
+        z.dense_idx = (int)((((long)z.oc * Cg + ic) * g.kernel_h + kh) * g.kernel_w + kw);
+        nzs->push_back(z);
+      }
+      g_rowptr[gi * Mg + i + 1] = (int)nzs->size();
+    }
+  }
+
+  escort_plan *p = new escort_plan();
+  memset(p, 0, sizeof(*p));
+  p->g = g;
+  p->Ho = Ho;
+  p->Wo = Wo;
+  p->nnz = nnz;
+  p->variant = -1;
+  p->host_nz = nzs;
+  cudaGetDevice(&p->device);
+
+  const int H = g.height, W = g.width;
+  std::vector<int4> meta(nnz), wmeta(nnz), tmeta(nnz);
+  std::vector<int> dense_idx(nnz), csr_pos(nnz), tsrc(nnz), colptr(g.channels + 1, 0);
+  for (long j = 0; j < nnz; ++j) {
+    const Nz &z = (*nzs)[j];
+    const int dy = z.kh * g.dilation_h - g.pad_h, dx = z.kw * g.dilation_w - g.pad_w;
+    meta[j] = make_int4(z.ic * H * W + dy * W + dx, dy, dx, __builtin_bit_cast(int, z.val));
+    wmeta[j] = make_int4(z.oc, z.ic, dy, dx);
+    dense_idx[j] = z.dense_idx;
+    csr_pos[j] = z.csr_pos;
+    colptr[z.ic + 1]++;
+  }
+  for (int c = 0; c < g.channels; ++c) colptr[c + 1] += colptr[c];
+  {
+    std::vector<int> cursor(colptr.begin(), colptr.end() - 1);
+    for (long j = 0; j < nnz; ++j) {
+      const Nz &z = (*nzs)[j];
+      const int t = cursor[z.ic]++;
+      tmeta[t] = make_int4(z.oc, z.kh * g.dilation_h - g.pad_h, z.kw * g.dilation_w - g.pad_w,
+                           __builtin_bit_cast(int, z.val));
+      tsrc[t] = (int)j;
+    }
+  }
+  int rc = 0;
+  if ((rc = upload(&p->d_rowptr, g_rowptr, stream)) || (rc = upload(&p->d_meta, meta, stream)) ||
+      (rc = upload(&p->d_dense_idx, dense_idx, stream)) || (rc = upload(&p->d_csr_pos, csr_pos, stream)) ||
+      (rc = upload(&p->d_colptr, colptr, stream)) || (rc = upload(&p->d_tmeta, tmeta, stream)) ||
+      (rc = upload(&p->d_tsrc, tsrc, stream)) || (rc = upload(&p->d_wmeta, wmeta, stream))) {
+    escort_plan_destroy(p);
+    return rc;
+  }
+  rc = tile_plan_build(p, -1, stream);
+  if (rc) {
+    escort_plan_destroy(p);
+    return rc;
+  }
+  ESCORT_CUDA(cudaStreamSynchronize(stream));  // host staging vectors go out of scope
+  *plan_out = p;
+  return 0;
+}
+
+extern "C" int escort_plan_destroy(escort_plan *p) {
+  if (!p) return 0;
+  cudaFree(p->d_rowptr);
+  cudaFree(p->d_meta);
+  cudaFree(p->d_dense_idx);
+  cudaFree(p->d_csr_pos);
+  cudaFree(p->d_colptr);
+  cudaFree(p->d_tmeta);
+  cudaFree(p->d_tsrc);
+  cudaFree(p->d_wmeta);
+  if (p->tile) tile_plan_free(p->tile);
+  delete p->host_nz;
+  delete p;
+  return 0;
+}
+
+extern "C" long escort_plan_nnz(const escort_plan *p) { return p ? p->nnz : -1; }
+
+extern "C" const char *escort_plan_kernel_name(const escort_plan *p) {
+  if (!p) return "null";
+  if (p->tile) return tile_kernel_name(p->tile);
+  return "sconv_fwd_generic";
+}
+
+extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
+  ESCORT_REQUIRE(p, "escort_plan_set_variant: null plan");
+  if (p->tile) {
+    tile_plan_free(p->tile);
+    p->tile = nullptr;
+  }
+  p->variant = variant;
+  if (variant == 0) return 0;
+  int rc = tile_plan_build(p, variant, 0);
+  if (rc) return rc;
+  ESCORT_CUDA(cudaStreamSynchronize(0));
+  if (variant > 0 && !p->tile) {
+    set_last_error("escort_plan_set_variant: geometry not supported by the requested tile variant");
+    return ESCORT_EINVAL;
+  }
+  return 0;
+}
+
+extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,
+                                    float *top, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && bottom && top && num >= 0, "escort_sconv_forward: bad arguments");
+  if (num == 0) return 0;
+  if (p->tile) return tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
+  const escort_geom &g = p->g;
+  dim3 grid(ceil_div(p->Ho * p->Wo, kGenThreads), g.num_output, num);
+  ESCORT_REQUIRE(num <= 65535, "escort_sconv_forward: batch too large for the generic kernel");
+  sconv_fwd_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_rowptr, p->d_meta, bottom, bias, fuse_relu, top,
+                                                             g.channels, g.height, g.width, g.num_output, p->Ho,
+                                                             p->Wo, g.stride_h, g.stride_w);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *top_diff, float *bottom_diff,
+                                          escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && top_diff && bottom_diff && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
+  if (num == 0) return 0;
+  const escort_geom &g = p->g;
+  dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
+  sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
+                                                                  g.channels, g.height, g.width, g.num_output, p->Ho,
+                                                                  p->Wo, g.stride_h, g.stride_w);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_sconv_backward_weight(escort_plan *p, int num, const float *bottom, const float *top_diff,
+                                            float *weight_diff_dense, float *weight_diff_csr, int accumulate,
+                                            escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && bottom && top_diff && num >= 0, "escort_sconv_backward_weight: bad arguments");
+  ESCORT_REQUIRE(weight_diff_dense || weight_diff_csr, "escort_sconv_backward_weight: no output buffer");
+  if (num == 0 || p->nnz == 0) return 0;
+  const escort_geom &g = p->g;
+  const int warps = 8;
+  const long blocks = (p->nnz + warps - 1) / warps;
+  sconv_bwd_weight_generic_kernel<<<(unsigned)blocks, warps * 32, 0, stream>>>(
+      p->nnz, p->d_wmeta, p->d_dense_idx, p->d_csr_pos, bottom, top_diff, num, g.channels, g.height, g.width,
+      g.num_output, p->Ho, p->Wo, g.stride_h, g.stride_w, weight_diff_dense, weight_diff_csr, accumulate);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_bias_backward(int num, int num_output, int out_spatial, const float *top_diff, float *bias_diff,
+                                    escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(top_diff && bias_diff && num >= 0 && num_output > 0 && out_spatial > 0,
+                 "escort_bias_backward: bad arguments");
+  if (num == 0) return 0;
+  bias_backward_kernel<<<num_output, 256, 0, stream>>>(num, num_output, out_spatial, top_diff, bias_diff);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense, float *values_csr,
+                                     escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && weights_dense, "escort_refresh_values: bad arguments");
+  if (p->nnz == 0) return 0;
+  const unsigned blocks = (unsigned)((p->nnz + 255) / 256);
+  refresh_kernel<<<blocks, 256, 0, stream>>>(p->nnz, weights_dense, p->d_dense_idx, p->d_csr_pos, p->d_meta, values_csr);
+  ESCORT_LAUNCH_CHECK();
+  refresh_t_kernel<<<blocks, 256, 0, stream>>>(p->nnz, p->d_meta, p->d_tsrc, p->d_tmeta);
+  ESCORT_LAUNCH_CHECK();
+  if (p->tile) return tile_refresh(p, weights_dense, stream);
+  return 0;
+}

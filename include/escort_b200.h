@@ -1,0 +1,153 @@
+/*
+ * escort_b200.h -- C ABI of the B200-native (sm_100a) Escort direct-sparse-convolution hot path.
+ *
+ * This is the drop-in boundary: every entry point below stands behind one reference interface (cited
+ * file:line, relative to chenxuhao/caffe-escoin).  Plain pointers and sizes only; all pointers are DEVICE
+ * pointers unless a name ends in _host.  `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream, which is what the reference uses everywhere).  Every function returns 0 on success, a positive
+ * cudaError_t value on a CUDA failure, or a negative ESCORT_E* code; nothing aborts, nothing calls
+ * cudaDeviceSynchronize (the reference's CudaTest() device sync after every launch,
+ * include/caffe/util/cutil_subset.h:28-38, is deliberately not reproduced).  The library is re-entrant; plans
+ * are bound to the device that was current when they were created.
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry point returns an error.
+ */
+#ifndef ESCORT_B200_H_
+#define ESCORT_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ESCORT_EINVAL (-1)   /* bad argument / unsupported geometry */
+#define ESCORT_ENOMEM (-2)   /* host allocation failed */
+#define ESCORT_ENCCL  (-3)   /* NCCL failure (see escort_last_error) */
+
+#if defined(__GNUC__)
+#define ESCORT_API __attribute__((visibility("default")))
+#else
+#define ESCORT_API
+#endif
+
+typedef void *escort_stream_t; /* cudaStream_t */
+
+/* Convolution geometry of one layer; field names follow BaseConvolutionLayer's members
+ * (include/caffe/layers/base_conv_layer.hpp:155-185; parsed in src/caffe/layers/base_conv_layer.cpp:276-446). */
+typedef struct escort_geom {
+  int channels;     /* conv_in_channels_  (C, all groups) */
+  int num_output;   /* conv_out_channels_ (M, all groups) */
+  int group;        /* group_ */
+  int height, width;          /* conv_input_shape_[1], [2] */
+  int kernel_h, kernel_w;     /* kernel_shape_ */
+  int pad_h, pad_w;           /* pad_ */
+  int stride_h, stride_w;     /* stride_ */
+  int dilation_h, dilation_w; /* dilation_ */
+} escort_geom;
+
+/* ---- a2: dense -> CSR ---------------------------------------------------------------------------------
+ * Replaces caffe_gpu_sparse_dense2csr<float> (include/caffe/util/math_functions.hpp:213-216,
+ * src/caffe/util/math_functions.cu:103-128, called at src/caffe/layers/base_conv_layer.cpp:240-246), whose
+ * cuSPARSE entry points no longer exist in CUDA 12.  Bit-exact with the CPU twin
+ * caffe_cpu_sparse_dense2csr<float> (src/caffe/util/math_functions.cpp:92-105): row-major M x N matrix A,
+ * keeps A[i][j] != 0 in (i, ascending j) order; rowptr has M+1 entries starting at 0; values / colidx must
+ * hold M*N entries (worst case, as the reference sizes them, base_conv_layer.cpp:509-512); nnz_per_row (M
+ * entries) may be NULL.  *nnz_total_host is written on the host after a stream synchronisation (the
+ * reference's call is synchronous too). */
+ESCORT_API int escort_pack_csr(int M, int N, const float *A, int *nnz_per_row, float *values, int *rowptr, int *colidx,
+                    int *nnz_total_host, escort_stream_t stream);
+
+/* ---- a3: stretch ---------------------------------------------------------------------------------------
+ * Replaces caffe_gpu_stretch (math_functions.hpp:226-228, math_functions.cu:706-727, called at
+ * base_conv_layer.cpp:263): in place, colidx (ic*kh*kw + r*kw + s) -> (ic*(H+pad_h) + r)*(W+pad_w) + s. */
+ESCORT_API int escort_stretch(const int *rowptr, int *colidx, int M, int height, int width, int pad_h, int pad_w,
+                   int kernel_h, int kernel_w, escort_stream_t stream);
+
+/* ---- a4: padded input copy ------------------------------------------------------------------------------
+ * Replaces copy_input_data<float> (math_functions.hpp:230-233, math_functions.cu:729-766, called at
+ * base_conv_layer.cpp:771,828): dst[(c*(H+ph)+y+ph)*(W+pw)+pw+x] = src[(c*H+y)*W+x].  Only needed by the
+ * compatibility entry escort_sconv_padded; the native forward reads the unpadded tensor. */
+ESCORT_API int escort_copy_input(float *dst, const float *src, int num_channels, int height, int width, int pad_h,
+                      int pad_w, escort_stream_t stream);
+
+/* ---- a6 (compat): caffe_gpu_sconv with the reference's exact argument list ------------------------------
+ * Replaces caffe_gpu_sconv<float> (math_functions.hpp:218-224, math_functions.cu:590-694, called at
+ * base_conv_layer.cpp:788-795,841): `input` is the top/left padded image(s), colidx is STRETCHED,
+ * out[oc,y,x] = (relu?)((fuse_relu ? bias[oc] : 0) + sum_j values[j]*input[y*sh*(W+pw) + x*sw + colidx[j]]).
+ * num > 1 processes `num` images spaced ifmap_size*num_groups floats apart on input and
+ * num_oc*num_groups*Ho*Wo on output (SCONV_PAR semantics, without the reference's odd-batch drop and
+ * grid bug, math_functions.cu:664,675-689).  Dilation != 1 uses the decode of sconv_dilation (:154-179). */
+ESCORT_API int escort_sconv_padded(int fuse_relu, int num, const float *input, int ifmap_size, const int *rowptr,
+                        const int *colidx, const float *values, const float *bias, int height, int width,
+                        int pad_h, int pad_w, int stride_h, int stride_w, int dilation_h, int dilation_w,
+                        int kernel_h, int kernel_w, float *output, int num_oc, int num_groups,
+                        escort_stream_t stream);
+
+/* ---- plans -----------------------------------------------------------------------------------------------
+ * State carried between WeightAlign and Forward/Backward: the derived, nnz-balanced blocked formats the
+ * fast kernels execute.  Built from the layer's CSR blobs in the reference's layout
+ * (base_conv_layer.cpp:240-246,509-513): values/colidx at offset (M/g)*(C/g)*kh*kw*g, rowptr at (M/g+1)*g
+ * (each group restarting at 0).  colidx may be raw (ic,kh,kw) columns (colidx_is_stretched = 0) or the
+ * stretched form (1).  The arrays are read during the call (device->host copy + stream sync) and not
+ * retained.  One plan per (layer, device); owned by the library. */
+typedef struct escort_plan escort_plan;
+
+ESCORT_API int escort_plan_create(const escort_geom *geom, const int *rowptr, const int *colidx, const float *values,
+                       int colidx_is_stretched, escort_plan **plan_out, escort_stream_t stream);
+ESCORT_API int escort_plan_destroy(escort_plan *plan);
+/* total nonzeros over all groups (sum of nz_num_, base_conv_layer.cpp:247) */
+ESCORT_API long escort_plan_nnz(const escort_plan *plan);
+/* name of the forward kernel variant the plan selected (static string) */
+ESCORT_API const char *escort_plan_kernel_name(const escort_plan *plan);
+/* tuning knob for tests/bench: force a forward variant (-1 auto, 0 generic, >0 tile-interpreter variants) */
+ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
+
+/* ---- a5-a9: native forward ---------------------------------------------------------------------------------
+ * Replaces the whole per-image sequence of ConvolutionLayer::Forward_gpu in SCONV / SCONV_PAR mode
+ * (src/caffe/layers/conv_layer.cu:15-26) = forward_gpu_sconv[_par] (base_conv_layer.cpp:749-848:
+ * copy_input_data + caffe_gpu_sconv per group) + forward_gpu_bias (:851-856), for the whole batch and all
+ * groups in one launch.  bottom: num x C x H x W unpadded NCHW; top: num x M x Ho x Wo; bias (M) nullable;
+ * fuse_relu applies max(.,0) in the epilogue (ConvolutionReLULayer, src/caffe/layers/conv_relu_layer.cu:8-30). */
+ESCORT_API int escort_sconv_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu,
+                         float *top, escort_stream_t stream);
+
+/* ---- a9: backward, restricted to the sparsity mask ------------------------------------------------------
+ * Caffe's contract (src/caffe/layers/conv_layer.cu:43-73, base_conv_layer.cpp:859-897): parameter diffs
+ * ACCUMULATE, bottom_diff is OVERWRITTEN.
+ * backward_data  : bottom_diff = W^T * top_diff           (replaces backward_gpu_gemm + col2im)
+ * backward_weight: gradient only at the plan's nonzero positions (replaces weight_gpu_gemm + im2col):
+ *                  weight_diff_dense (M x C/g x kh x kw, nullable) gets += at mask positions;
+ *                  weight_diff_csr (nullable) gets the same numbers in CSR order, in the reference blob
+ *                  layout (group g at offset weight_offset*g), overwritten if accumulate == 0 else +=.
+ * bias_backward  : bias_diff[oc] += sum_{n,y,x} top_diff  (replaces backward_gpu_bias gemv). */
+ESCORT_API int escort_sconv_backward_data(escort_plan *plan, int num, const float *top_diff, float *bottom_diff,
+                               escort_stream_t stream);
+ESCORT_API int escort_sconv_backward_weight(escort_plan *plan, int num, const float *bottom, const float *top_diff,
+                                 float *weight_diff_dense, float *weight_diff_csr, int accumulate,
+                                 escort_stream_t stream);
+ESCORT_API int escort_bias_backward(int num, int num_output, int out_spatial, const float *top_diff, float *bias_diff,
+                         escort_stream_t stream);
+
+/* Re-gather CSR values from the (updated) dense weights at the plan's fixed positions, into the plan and
+ * optionally into the layer's nz_weight_values_ blob (values_csr nullable).  The reference never refreshes
+ * its CSR after a solver update; the masked training step needs it. */
+ESCORT_API int escort_refresh_values(escort_plan *plan, const float *weights_dense, float *values_csr,
+                          escort_stream_t stream);
+
+/* ---- e: multi-GPU gradient exchange ------------------------------------------------------------------------
+ * Replaces NCCL<Dtype>::on_gradients_ready (src/caffe/parallel.cpp:238-256): ncclAllReduce(sum) over the
+ * flat diff buffer, then scale by `scale` (1/solver_count).  `comm` is an ncclComm_t passed as void*. */
+ESCORT_API int escort_allreduce_grads(void *comm, float *flat, size_t count, float scale, escort_stream_t stream);
+
+/* ---- misc ---------------------------------------------------------------------------------------------------- */
+/* register-resident FFMA microbenchmark used for the FP32 roofline denominator;
+ * returns achieved TFLOP/s in *tflops_host, SM count and SM clock (kHz, from device attributes). */
+ESCORT_API int escort_measure_fp32_peak(int variant, int iters, double *tflops_host, int *sm_count_host, int *clock_khz_host);
+ESCORT_API const char *escort_last_error(void);
+ESCORT_API const char *escort_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ESCORT_B200_H_ */

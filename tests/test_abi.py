@@ -1,0 +1,59 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol include/escort_b200.h
+declares; argument validation returns error codes instead of aborting (no compute is launched without a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    return C.CDLL(os.path.join(ROOT, "caffe_escoin_b200", "libescort_b200.so"))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "escort_b200.h")).read()
+    return sorted(set(re.findall(r"ESCORT_API[^;(]*?\b(escort_\w+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_surface():
+    syms = declared_symbols()
+    for s in ("escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
+              "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
+              "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), "missing export " + s
+
+
+def test_python_binding_lists_every_declared_symbol(lib):
+    from caffe_escoin_b200 import capi
+    assert sorted(capi.EXPORTS) == declared_symbols()
+
+
+def test_bad_arguments_return_codes_not_aborts(lib):
+    lib.escort_last_error.restype = C.c_char_p
+    assert lib.escort_pack_csr(0, 0, None, None, None, None, None, None, None) == -1
+    assert b"escort_pack_csr" in lib.escort_last_error()
+    assert lib.escort_plan_create(None, None, None, None, 0, None, None) == -1
+    assert lib.escort_sconv_forward(None, 1, None, None, 0, None, None) == -1
+    assert lib.escort_plan_destroy(None) == 0
+    assert lib.escort_allreduce_grads(None, None, C.c_size_t(0), C.c_float(1.0), None) == 0
+
+
+def test_product_package_does_not_import_the_oracle():
+    """The oracle is test infrastructure; nothing under caffe_escoin_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "caffe_escoin_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "pyoracle" not in txt and "escort_oracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)

@@ -468,8 +468,9 @@ extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,
                                     float *top, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  ESCORT_REQUIRE(p && bottom && top && num >= 0, "escort_sconv_forward: bad arguments");
-  if (num == 0) return 0;
+  ESCORT_REQUIRE(p && num >= 0, "escort_sconv_forward: bad arguments");
+  if (num == 0) return 0;  // empty batch: nothing to do (pointers may be null)
+  ESCORT_REQUIRE(bottom && top, "escort_sconv_forward: null tensor");
   if (p->tile) return tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(p->Ho * p->Wo, kGenThreads), g.num_output, num);
@@ -484,8 +485,9 @@ extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom
 extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *top_diff, float *bottom_diff,
                                           escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  ESCORT_REQUIRE(p && top_diff && bottom_diff && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
+  ESCORT_REQUIRE(p && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
   if (num == 0) return 0;
+  ESCORT_REQUIRE(top_diff && bottom_diff, "escort_sconv_backward_data: null tensor");
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
   sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
@@ -499,9 +501,10 @@ extern "C" int escort_sconv_backward_weight(escort_plan *p, int num, const float
                                             float *weight_diff_dense, float *weight_diff_csr, int accumulate,
                                             escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  ESCORT_REQUIRE(p && bottom && top_diff && num >= 0, "escort_sconv_backward_weight: bad arguments");
+  ESCORT_REQUIRE(p && num >= 0, "escort_sconv_backward_weight: bad arguments");
   ESCORT_REQUIRE(weight_diff_dense || weight_diff_csr, "escort_sconv_backward_weight: no output buffer");
   if (num == 0 || p->nnz == 0) return 0;
+  ESCORT_REQUIRE(bottom && top_diff, "escort_sconv_backward_weight: null tensor");
   const escort_geom &g = p->g;
   const int warps = 8;
   const long blocks = (p->nnz + warps - 1) / warps;

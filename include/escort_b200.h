@@ -100,6 +100,8 @@ ESCORT_API int escort_plan_destroy(escort_plan *plan);
 ESCORT_API long escort_plan_nnz(const escort_plan *plan);
 /* name of the forward kernel variant the plan selected (static string) */
 ESCORT_API const char *escort_plan_kernel_name(const escort_plan *plan);
+/* human-readable tiling summary of the selected forward kernel, written to buf (NUL terminated) */
+ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen);
 /* tuning knob for tests/bench: force a forward variant (-1 auto, 0 generic, >0 tile-interpreter variants) */
 ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
 

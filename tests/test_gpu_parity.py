@@ -87,14 +87,20 @@ def test_pack_full_size_layers_bit_exact(capi, po):
 
 
 # ---------------------------------------------------------------- forward (a4-a9)
-def run_forward_all_paths(capi, po, g, w, bias, x, relu, variants=(-1, 0)):
+def run_forward_all_paths(capi, po, g, w, bias, x, relu, variants=None):
+    """Every forward kernel that accepts the geometry: auto choice (-1), generic (0), each tile-interpreter variant."""
     geom = capi_geom(capi, g)
     csr = capi.weight_align(to_dev(w), geom)
     outs = {}
+    if variants is None:
+        variants = list(range(-1, 32))
     for v in variants:
         plan = capi.Plan(geom, csr)
         if v != -1:
-            plan.set_variant(v)
+            try:
+                plan.set_variant(v)
+            except capi.EscortError:
+                continue   # tile variant does not apply to this kernel size / stride
         y = plan.forward(to_dev(x), to_dev(bias), relu=relu)
         _torch().cuda.synchronize()
         outs["%d:%s" % (v, plan.kernel_name)] = y.cpu().numpy()

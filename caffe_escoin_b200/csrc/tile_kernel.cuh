@@ -1,186 +1,263 @@
-// tile_kernel.cuh -- device side of the tile-interpreter forward kernel (see sconv_tile.cu for the design).
+// tile_kernel.cuh -- device side of the tile-interpreter forward kernel (design notes in sconv_tile.cu).
 #pragma once
 #include "common.cuh"
 
 namespace escort {
 
 static constexpr int kLoaderUnroll = 8;
+static constexpr int kMaxStages = 8;
+static constexpr int kBarBytes = 256;  // mbarrier area at the start of dynamic shared memory
 
 struct TileParams {
   // geometry
   int C, H, W, M, Ho, Wo, pad_h, pad_w;
-  int Cg, Mg;              // channels / outputs per conv group
+  int Cg, Mg, ngroups;     // channels / outputs per conv group, number of conv groups
   // tiling
-  int G, BR, PX, PY, nbands;
+  int G, GP;               // images per CTA, image slots per CTA (= G / PAIR)
+  int BR, PX, PY, nbands;  // patch rows per band, patch grid, bands per image
   int WP, WO;              // pixel warps x channel-block warps (WP*WO == NCW of the variant)
-  int R, P;                // smem rows per plane, pitch (floats)
+  int R, P;                // staged rows per plane, row pitch in positions
+  int plane_f;             // floats per (channel, image slot) plane = R*P*PAIR + skew
   int CI, nchunks;         // channels per chunk, chunks per conv group
-  int nblk;                // channel blocks per conv group
-  int ogroups;             // ceil(nblk / WO) per conv group
+  int nblk, ogroups;       // channel blocks per conv group, CTAs' channel-block groups per conv group
   int nslots;              // valid lane slots per CTA (<= WP*32)
-  int chunk_floats;        // CI*G*R*P
-  int n_igroups;
+  // pipeline
+  int NS;                  // stages
+  int stage0_off;          // byte offset of stage 0 in dynamic smem
+  int stage_bytes;         // input area + program area
+  int in_bytes;            // CI * GP * plane_f * 4
+  int hdr_bytes;           // program-region header (segment offsets), multiple of 16
+  int n_igroups;           // filled per launch
+  int n4;                  // loader: 16-byte words per plane window = (R*W + 6)/4 + 1
+  unsigned n4_magic, ci_magic;  // ceil(2^32 / n4), ceil(2^32 / CI) for multiply-high division
   // tables
-  const int4 *lanes;       // [WP*32] {lane_base_bytes, g, pyb, px}
-  const int *oc_list;      // [group*nblk*OT] global out-channel or -1
-  const uint2 *prog;       // records
-  const int *seg;          // [group*nblk*nchunks] record offset of segment
-  const unsigned short *dst_off;  // [R*W] smem float offset of element e of a plane band (row-major, W wide)
+  const int4 *lanes;       // [WP*32] {lane_base_bytes, image slot, pyb, px}
+  const int *oc_list;      // [ngroups*nblk*OT] global out-channel or -1
+  const uint4 *prog;       // program regions (16-byte units)
+  const int2 *rtab;        // [ngroups*ogroups*nchunks] {offset, length} of a region in 16-byte units
+  const unsigned short *dst_off;  // [R*W] position offset of element e of a plane band (row-major, W wide)
 };
 
 #ifndef ESCORT_TILE_DEVICE_ONLY
 struct TilePlan {
   int vidx;                // index into the variant table
   const char *name;
-  int OT, TY, TX, KH, KW, S;
+  int OT, TY, TX, KH, KW, S, PAIR;
   TileParams prm;
   size_t smem_bytes;
-  dim3 grid;
   int4 *d_lanes;
   int *d_oc_list;
-  uint2 *d_prog;
-  int *d_seg;
+  uint4 *d_prog;
+  int2 *d_rtab;
   unsigned short *d_dst_off;
-  int *d_prog_pos;         // [nnz] row-major nonzero -> record index (for value refresh)
+  int *d_prog_pos;         // [nnz] row-major nonzero -> index of its record (8-byte units) in d_prog
   size_t nrecords;
+  int num_sms;
 };
 #endif
 
 #ifndef ESCORT_TILE_HOST_ONLY
-// ------------------------------------------------------------------------------------------------------
-// loader: copy one chunk (CI channels x G images, the band's input rows) into a smem buffer, interior only
-// ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_chunk(const TileParams &p, const float *__restrict__ bottom, float *buf,
-                                           const unsigned short *dst_off_s, int n0, int num, int cbase, int cend,
-                                           int ylo, int nrows, int rowshift, int wid, int nw, int lane) {
+// ---- mbarrier helpers (CTA scope) ---------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+
+struct UnitCoord {
+  int og, cg, band, n0;
+};
+__device__ __forceinline__ UnitCoord decode_unit(const TileParams &p, int u) {
+  // u = ((igroup * nbands + band) * ngroups + cg) * ogroups + og  -- og fastest: CTAs that share an input tile run
+  // at the same time and hit it in L2
+  UnitCoord c;
+  c.og = u % p.ogroups; u /= p.ogroups;
+  c.cg = u % p.ngroups; u /= p.ngroups;
+  c.band = u % p.nbands; u /= p.nbands;
+  c.n0 = u * p.G;
+  return c;
+}
+
+// loader: copy one chunk (CI channels x G images, the band's input rows) into a stage, interior only.
+// Every (image, channel) plane band is one contiguous run of nrows*W floats in the NCHW tensor.  It is copied with
+// 4-byte cp.async (LDGSTS): global -> shared without staging registers, so a loader warp keeps hundreds of
+// requests in flight (the copy is latency bound; memory-level parallelism is what matters) and scatters straight
+// into the padded, optionally image-interleaved, shared layout through the dst_off table.  Completion is tracked
+// by the stage's "full" mbarrier via cp.async.mbarrier.arrive.noinc, so the loader never waits for its own loads.
+__device__ __forceinline__ void cp_async4(unsigned dst_smem, const float *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+template <int PAIR>
+__device__ __forceinline__ void load_chunk(const TileParams &p, const float *__restrict__ bottom, float *in_s,
+                                           unsigned in_s_addr, const unsigned short *dst_off_s, int n0, int num,
+                                           int cbase, int cend, int ylo, int nrows, int rowshift, bool zero_rows, int lw,
+                                           int nlw, int lane) {
   const int L = nrows * p.W;
   const int nplanes = p.CI * p.G;
-  for (int pl = wid; pl < nplanes; pl += nw) {
-    const int ci = pl / p.G, g = pl - ci * p.G;
+  const size_t plane_stride = (size_t)p.H * p.W;  // floats between channels
+  for (int pl = lw; pl < nplanes; pl += nlw) {
+    const int g = pl / p.CI, ci = pl - g * p.CI;
     const int c = cbase + ci, n = n0 + g;
-    if (c >= cend || n >= num) continue;
-    const float *src = bottom + (((size_t)n * p.C + c) * p.H + ylo) * p.W;
-    float *dst = buf + (size_t)pl * p.R * p.P + rowshift * p.P;
-    for (int e0 = 0; e0 < L; e0 += 32 * kLoaderUnroll) {
-      float v[kLoaderUnroll];
-#pragma unroll
-      for (int u = 0; u < kLoaderUnroll; ++u) {
-        const int e = e0 + u * 32 + lane;
-        v[u] = (e < L) ? __ldg(src + e) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < kLoaderUnroll; ++u) {
-        const int e = e0 + u * 32 + lane;
-        if (e < L) dst[dst_off_s[e]] = v[u];
-      }
+    const int plane_off = (ci * p.GP + g / PAIR) * p.plane_f + (g % PAIR);  // floats
+    if (zero_rows) {
+      // rows outside the image differ between bands: rewrite them as zeros (only when the layer is banded)
+      float *plane = in_s + plane_off;
+      const int lo_end = rowshift * p.P, hi_beg = (rowshift + nrows) * p.P, tot = p.R * p.P;
+      for (int i = lane; i < lo_end; i += 32) plane[i * PAIR] = 0.f;
+      for (int i = hi_beg + lane; i < tot; i += 32) plane[i * PAIR] = 0.f;
     }
+    if (c >= cend || n >= num) continue;
+    const float *src = bottom + ((size_t)n * p.C + c) * plane_stride + (size_t)ylo * p.W;
+    const unsigned dst = in_s_addr + 4u * (unsigned)(plane_off + rowshift * p.P * PAIR);
+#pragma unroll 4
+    for (int e = lane; e < L; e += 32) cp_async4(dst + (unsigned)dst_off_s[e] * (4u * PAIR), src + e);
   }
 }
 
-template <int OT, int TY, int TX, int KH, int KW, int S>
-__global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S>::NCW + Interp<OT, TY, TX, KH, KW, S>::NLW) * 32, 1)
+template <int OT, int TY, int TX, int KH, int KW, int S, int PAIR>
+__global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + Interp<OT, TY, TX, KH, KW, S, PAIR>::NLW) * 32, 1)
     sconv_tile_kernel(const TileParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias,
-                      int fuse_relu, float *__restrict__ top) {
-  using IP = Interp<OT, TY, TX, KH, KW, S>;
-  constexpr int kComputeWarps = IP::NCW, kLoaderWarps = IP::NLW, kTileThreads = (IP::NCW + IP::NLW) * 32;
-  extern __shared__ float4 smem_f4[];
-  float *smem = reinterpret_cast<float *>(smem_f4);
-  float *buf0 = smem;
-  float *buf1 = smem + p.chunk_floats;
-  unsigned short *dst_off_s = reinterpret_cast<unsigned short *>(smem + 2 * (size_t)p.chunk_floats);
-
+                      int fuse_relu, float *__restrict__ top, int nunits) {
+  using IP = Interp<OT, TY, TX, KH, KW, S, PAIR>;
+  constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = (NCW + NLW) * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  unsigned short *dst_off_s = reinterpret_cast<unsigned short *>(smem_raw + kBarBytes);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  // unit decode: blockIdx.x = ((igroup * nbands + band) * group + cg) * ogroups + og   (og fastest: CTAs that share
-  // the same input tile are launched together and hit it in L2)
-  int u = blockIdx.x;
-  const int og = u % p.ogroups; u /= p.ogroups;
-  const int ngroups = p.C / p.Cg;
-  const int cg = u % ngroups; u /= ngroups;
-  const int band = u % p.nbands; u /= p.nbands;
-  const int n0 = u * p.G;
+  const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
 
-  // band input rows: smem row r <-> input row y_in0 + r
-  const int y_in0 = band * p.BR * TY * S - p.pad_h;
-  const int ylo = max(0, y_in0);
-  const int yhi = min(p.H, y_in0 + p.R);
-  const int nrows = max(0, yhi - ylo);
-  const int rowshift = ylo - y_in0;
-
-  // zero both buffers once (halo), stage the loader's scatter table
-  {
-    float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int n4 = (2 * p.chunk_floats) >> 2;
-    for (int i = tid; i < n4; i += kTileThreads) smem_f4[i] = z;
-    const int ntab = p.R * p.W;
-    for (int i = tid; i < ntab; i += kTileThreads) dst_off_s[i] = p.dst_off[i];
-  }
-  __syncthreads();
-  const int cbase0 = cg * p.Cg, cend = cbase0 + p.Cg;
-  load_chunk(p, bottom, buf0, dst_off_s, n0, num, cbase0, cend, ylo, nrows, rowshift, wid, kComputeWarps + kLoaderWarps,
-             lane);
-  __syncthreads();
-
-  const bool is_loader = wid >= kComputeWarps;
-  // compute-warp role
-  const int pw = wid % p.WP;            // pixel warp
-  const int ow = wid / p.WP;            // channel-block warp (valid for compute warps)
-  const int blk = og * p.WO + ow;       // channel block within the conv group
-  const bool blk_valid = !is_loader && blk < p.nblk;
-  int4 li = make_int4(0, 0, 0, 0);
-  if (!is_loader) li = p.lanes[pw * 32 + lane];
-
-  float acc[IP::NACC];
-#pragma unroll
-  for (int i = 0; i < IP::NACC; ++i) acc[i] = 0.f;
-
-  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem);
-  const unsigned pitch_bytes = (unsigned)p.P * 4u;
-  const int *seg = p.seg + ((size_t)cg * p.nblk + (blk_valid ? blk : 0)) * p.nchunks;
-
-  for (int c = 0; c < p.nchunks; ++c) {
-    if (is_loader) {
-      if (c + 1 < p.nchunks)
-        load_chunk(p, bottom, ((c + 1) & 1) ? buf1 : buf0, dst_off_s, n0, num, cbase0 + (c + 1) * p.CI, cend, ylo,
-                   nrows, rowshift, wid - kComputeWarps, kLoaderWarps, lane);
-    } else if (blk_valid) {
-      const unsigned lane_base = smem_base + ((c & 1) ? (unsigned)p.chunk_floats * 4u : 0u) + (unsigned)li.x;
-      IP::run(acc, p.prog + seg[c], lane_base, pitch_bytes);
+  // one-time set-up: barriers, zero halo (all stages), loader scatter table
+  if (tid == 0) {
+    for (int s = 0; s < p.NS; ++s) {
+      mbar_init(full_bar + 8 * s, NLW * 32);
+      mbar_init(empty_bar + 8 * s, NCW);
     }
-    __syncthreads();
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    float4 *st4 = reinterpret_cast<float4 *>(smem_raw + p.stage0_off);
+    const int n4 = (p.NS * p.stage_bytes) >> 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n4; i += NT) st4[i] = z;
+    const int ntab = p.R * p.W;
+    for (int i = tid; i < ntab; i += NT) dst_off_s[i] = p.dst_off[i];
+  }
+  __syncthreads();
+
+  if (wid >= NCW) {
+    // ================= loader warps: stream input chunks + byte-code regions through the stage ring ==========
+    const int lw = wid - NCW;
+    int it = 0;
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      const UnitCoord uc = decode_unit(p, u);
+      const int y_in0 = uc.band * p.BR * TY * S - p.pad_h;  // smem row r <-> input row y_in0 + r
+      const int ylo = max(0, y_in0), yhi = min(p.H, y_in0 + p.R);
+      const int nrows = max(0, yhi - ylo), rowshift = ylo - y_in0;
+      const int cbase0 = uc.cg * p.Cg, cend = cbase0 + p.Cg;
+      const int2 *rt = p.rtab + ((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks;
+      for (int c = 0; c < p.nchunks; ++c, ++it) {
+        const int s = it % p.NS, k = it / p.NS;
+        if (k > 0) mbar_wait(empty_bar + 8 * s, (unsigned)((k - 1) & 1));
+        unsigned char *stage = smem_raw + p.stage0_off + (size_t)s * p.stage_bytes;
+        const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
+        load_chunk<PAIR>(p, bottom, reinterpret_cast<float *>(stage), stage_addr, dst_off_s, uc.n0, num,
+                         cbase0 + c * p.CI, cend, ylo, nrows, rowshift, p.nbands > 1, lw, NLW, lane);
+        {  // byte-code region of this (channel-block group, chunk): contiguous 16-byte async copies
+          const int2 r = rt[c];
+          const uint4 *src = p.prog + r.x;
+          const unsigned dst = stage_addr + p.in_bytes;
+          for (int i = lw * 32 + lane; i < r.y; i += NLW * 32) cp_async16(dst + 16u * i, src + i);
+        }
+        // every loader thread arrives once its own cp.asyncs have landed (noinc: counted in the init count)
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar + 8 * s) : "memory");
+      }
+    }
+    return;
   }
 
-  // epilogue: bias + ReLU fused, predicated stores
-  if (blk_valid) {
-    const int g = li.y, pyb = li.z, px = li.w;
-    const int n = n0 + g;
-    const int y0 = (band * p.BR + pyb) * TY, x0 = px * TX;
+  // ================= compute warps ============================================================================
+  // (kept deliberately lean: everything that is live across the interpreter block costs a register on top of the
+  // accumulators, so unit coordinates and the lane record are recomputed in the epilogue instead of kept)
+  const unsigned lane_base_off = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+  const unsigned pitch_bytes = (unsigned)p.P * 4u * PAIR;
+  float acc[IP::NACC];
+  unsigned s = 0, ph = 0;
+  const unsigned ow4 = 4u * (unsigned)(wid / p.WP);
+#pragma unroll 1
+  for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+#pragma unroll
+    for (int i = 0; i < IP::NACC; ++i) acc[i] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < p.nchunks; ++c) {
+      mbar_wait(full_bar + 8 * s, ph);
+      {
+        // channel blocks past the end of the layer own an empty segment (a lone END record), so the interpreter
+        // block is entered unconditionally and appears exactly once in the kernel
+        const unsigned stage = smem_base + p.stage0_off + s * p.stage_bytes;
+        const unsigned region = stage + p.in_bytes;
+        unsigned seg;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(seg) : "r"(region + ow4));
+        IP::run(acc, region + seg, stage + lane_base_off, pitch_bytes);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(empty_bar + 8 * s);
+      if (++s == (unsigned)p.NS) {
+        s = 0;
+        ph ^= 1u;
+      }
+    }
+    // epilogue: bias + ReLU fused, predicated stores
+    const UnitCoord uc = decode_unit(p, u);
+    const int pw = wid % p.WP, ow = wid / p.WP;
+    const int blk = uc.og * p.WO + ow;
     const int slot = pw * 32 + lane;
-    if (slot < p.nslots && n < num && pyb < p.BR) {
+    if (blk < p.nblk && slot < p.nslots) {
+      const int4 li = p.lanes[slot];
+      const int gs = li.y, pyb = li.z, px = li.w;
+      const int y0 = (uc.band * p.BR + pyb) * TY, x0 = px * TX;
 #pragma unroll
       for (int o = 0; o < OT; ++o) {
-        const int oc = p.oc_list[((size_t)cg * p.nblk + blk) * OT + o];
+        const int oc = p.oc_list[((size_t)uc.cg * p.nblk + blk) * OT + o];
         if (oc < 0) continue;
         const float b = bias ? __ldg(bias + oc) : 0.f;
-        float *out = top + (((size_t)n * p.M + oc) * p.Ho) * p.Wo;
 #pragma unroll
-        for (int ty = 0; ty < TY; ++ty) {
-          const int y = y0 + ty;
-          if (y >= p.Ho) continue;
+        for (int im = 0; im < PAIR; ++im) {
+          const int n = uc.n0 + gs * PAIR + im;
+          if (n >= num) continue;
+          float *out = top + (((size_t)n * p.M + oc) * p.Ho) * p.Wo;
 #pragma unroll
-          for (int tx = 0; tx < TX; ++tx) {
-            const int x = x0 + tx;
-            if (x >= p.Wo) continue;
-            float v = acc[(o * TY + ty) * TX + tx] + b;
-            if (fuse_relu) v = fmaxf(v, 0.f);
-            out[(size_t)y * p.Wo + x] = v;
+          for (int ty = 0; ty < TY; ++ty) {
+            const int y = y0 + ty;
+            if (y >= p.Ho) continue;
+#pragma unroll
+            for (int tx = 0; tx < TX; ++tx) {
+              const int x = x0 + tx;
+              if (x >= p.Wo) continue;
+              float v = acc[((o * TY + ty) * TX + tx) * PAIR + im] + b;
+              if (fuse_relu) v = fmaxf(v, 0.f);
+              out[(size_t)y * p.Wo + x] = v;
+            }
           }
         }
       }
     }
   }
 }
-
-
 #endif  // !ESCORT_TILE_HOST_ONLY
 
 }  // namespace escort

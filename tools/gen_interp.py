@@ -1,14 +1,19 @@
 #!/usr/bin/env python
-"""Generate the inline-PTX "tile interpreter" inner loops of caffe_escoin_b200/csrc/sconv_tile.cu.
+"""Generate the inline-PTX "tile interpreter" inner loops of caffe_escoin_b200/csrc/tile_kernel.cuh.
 
 Why generated PTX: the hot loop of the direct sparse convolution must keep an OT x TY x TX block of output
 accumulators in REGISTERS and apply each nonzero weight (oc, ic, kh, kw) to it with the input patch also in
-registers (one shared-memory load per ~4+ FMAs instead of one per FMA).  Which accumulators a nonzero touches
-is data dependent, and registers cannot be indexed dynamically, so the kernel is a threaded-code interpreter:
-every (oc_local, kh, kw) combination has its own straight-line handler (TY*TX FFMAs on fixed registers) and
-the pruned weights are compiled, at plan time, into a byte-code stream of {weight, handler id} records that
-each warp walks with a `brx.idx` indirect branch.  CUDA C++ cannot express this (a `switch` is lowered to a
-compare tree), hence one generated asm block per tile shape.
+registers (one shared-memory load per several FMAs instead of one per FMA, which is what caps the reference's
+sconv_shm kernel).  Which accumulators a nonzero touches is data dependent, and registers cannot be indexed
+dynamically, so the kernel is a threaded-code interpreter: every (oc_local, kh, kw) combination has its own
+straight-line handler (TY*TX FMAs on fixed registers) and the pruned weights are compiled, at plan time, into
+a byte-code stream of {weight, handler id} records that each warp walks with a `brx.idx` indirect branch.
+CUDA C++ cannot express this (a `switch` is lowered to a compare tree), hence one generated asm block per
+tile shape.
+
+PAIR = 2 variants process two images per lane with the packed `fma.rn.f32x2` (FFMA2, new on sm_100): the two
+images are interleaved as float2 in shared memory, so a 128-bit shared load yields two register pairs and one
+issue slot does two FMAs -- the dispatch overhead then hides under the FMA pipe instead of competing with it.
 
 Usage: python tools/gen_interp.py   (writes caffe_escoin_b200/csrc/generated/interp_v<k>.inc + variant_list.inc)
 """
@@ -18,83 +23,134 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUTDIR = os.path.join(ROOT, "caffe_escoin_b200", "csrc", "generated")
 
-# (OT, TY, TX, KH, KW, S, NCW, NLW): tile shape, kernel taps, stride, compute warps, loader warps.
-# 8 warps/CTA (2 per SM sub-partition) allow 255 registers; 12 warps/CTA allow 168.
+# (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW): channel block, tile, kernel taps, stride, images per lane,
+# compute warps, loader warps.  8 warps/CTA (2 per SM sub-partition) allow 255 registers; 12 allow 168.
 VARIANTS = [
-    (8, 4, 4, 3, 3, 1, 6, 2),
-    (8, 2, 4, 3, 3, 1, 10, 2),
-    (4, 4, 4, 3, 3, 1, 10, 2),
-    (16, 1, 4, 3, 3, 1, 10, 2),
-    (8, 2, 4, 5, 5, 1, 6, 2),
-    (4, 4, 4, 5, 5, 1, 6, 2),
-    (8, 4, 4, 1, 1, 1, 6, 2),
-    (8, 2, 4, 1, 1, 1, 10, 2),
-    (8, 2, 4, 3, 3, 2, 6, 2),
-    (4, 4, 4, 3, 3, 2, 6, 2),
+    # 3x3 stride 1
+    (8, 2, 4, 3, 3, 1, 1, 16, 4),
+    (4, 2, 4, 3, 3, 1, 1, 20, 4),
+    (4, 4, 4, 3, 3, 1, 1, 14, 2),
+    (8, 4, 4, 3, 3, 1, 1, 6, 2),
+    (2, 4, 4, 3, 3, 1, 1, 16, 4),
+    (4, 2, 4, 3, 3, 1, 2, 14, 2),
+    (4, 4, 4, 3, 3, 1, 2, 6, 2),
+    (8, 2, 4, 3, 3, 1, 2, 6, 2),
+    # 5x5 stride 1
+    (4, 2, 4, 5, 5, 1, 1, 14, 2),
+    (4, 4, 4, 5, 5, 1, 1, 6, 2),
+    (4, 2, 4, 5, 5, 1, 2, 6, 2),
+    # 1x1
+    (8, 2, 4, 1, 1, 1, 1, 16, 4),
+    (8, 2, 4, 1, 1, 1, 2, 6, 2),
+    # 3x3 stride 2
+    (8, 2, 4, 3, 3, 2, 1, 14, 2),
+    (4, 2, 4, 3, 3, 2, 2, 6, 2),
 ]
 
 
-def gen_variant(OT, TY, TX, KH, KW, S, NCW, NLW):
-    NACC = OT * TY * TX
+def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
+    NACC = OT * TY * TX               # accumulator registers (32-bit for PAIR 1, 64-bit pairs for PAIR 2)
     PR = (TY - 1) * S + KH            # patch rows held in registers
     PC = (TX - 1) * S + KW            # patch cols needed
-    PCV = (PC + 3) // 4               # 128-bit loads per patch row
-    XW = PCV * 4
+    per_vec = 4 // PAIR               # positions per 128-bit shared load
+    half = per_vec // 2               # positions per 64-bit shared load (0 for PAIR 2: one position = 64 bits)
+    # per-row load plan: 128-bit loads, with a 64-bit tail when that saves registers
+    loads = []                        # (position offset, positions)
+    pos = 0
+    while pos < PC:
+        rem = PC - pos
+        if PAIR == 1 and rem <= 2:
+            loads.append((pos, 2)); pos += 2
+        elif PAIR == 2 and rem == 1:
+            loads.append((pos, 1)); pos += 1
+        else:
+            loads.append((pos, per_vec)); pos += per_vec
+    XW = pos                          # positions per patch row actually loaded
     NX = PR * XW
     NC = OT * KH * KW
     L = []
     a = L.append
     a("{")
-    a(".reg .f32 x<%d>;" % NX)
-    a(".reg .b32 wcur, ccur, wnxt, cnxt, ad<%d>;" % PR)
-    a(".reg .b64 pc;")
-    a("mov.b64 pc, %%%d;" % NACC)
-    a("ld.global.nc.v2.b32 {wcur, ccur}, [pc];")
-    a("ld.global.nc.v2.b32 {wnxt, cnxt}, [pc+8];")
-    a("add.s64 pc, pc, 16;")
+    NOPS = NACC * PAIR                # "+f" operands
+    if PAIR == 1:
+        a(".reg .f32 x<%d>;" % NX)
+    else:
+        a(".reg .b64 x<%d>, ww, a<%d>;" % (NX, NACC))
+        for i in range(NACC):
+            a("mov.b64 a%d, {%%%d, %%%d};" % (i, 2 * i, 2 * i + 1))
+    a(".reg .b32 wcur, wnxt, cnxt, wnn, cnn, ctmp, pc, ad<%d>;" % PR)
+    # Threaded code.  Register protocol at a handler's entry: wcur = payload of the record being executed,
+    # (wnxt, cnxt) = the following record (cnxt = which handler runs next), pc -> the record after that.
+    # Each handler first fetches record i+2 into (wnn, cnn) so the shared-memory latency and the jump-table lookup
+    # for cnxt both overlap its FMAs, then rotates the registers and branches with its own brx.idx.
+    a("mov.u32 pc, %%%d;" % NOPS)
+    a("ld.shared.v2.b32 {wcur, ctmp}, [pc];")
+    a("ld.shared.v2.b32 {wnxt, cnxt}, [pc+8];")
+    a("add.u32 pc, pc, 16;")
     targets = ["HF%d" % c for c in range(NC)] + ["HLOAD", "HEND"]
     a("TL: .branchtargets %s;" % ", ".join(targets))
-    a("brx.idx ccur, TL;")
-    adv = ["mov.b32 wcur, wnxt;", "mov.b32 ccur, cnxt;", "ld.global.nc.v2.b32 {wnxt, cnxt}, [pc];",
-           "add.s64 pc, pc, 8;", "brx.idx ccur, TL;"]
+    a("brx.idx ctmp, TL;")
+    fetch = "ld.shared.v2.b32 {wnn, cnn}, [pc];"
+    adv = ["mov.b32 wcur, wnxt;", "mov.b32 wnxt, wnn;", "mov.b32 ctmp, cnxt;", "mov.b32 cnxt, cnn;",
+           "add.u32 pc, pc, 8;", "brx.idx ctmp, TL;"]
     for c in range(NC):
         o, kh, kw = c // (KH * KW), (c // KW) % KH, c % KW
         a("HF%d:" % c)
+        a(fetch)
+        if PAIR == 2:
+            a("mov.b64 ww, {wcur, wcur};")
         for ty in range(TY):
             for tx in range(TX):
                 acc = (o * TY + ty) * TX + tx
                 xi = (ty * S + kh) * XW + tx * S + kw
-                a("fma.rn.f32 %%%d, wcur, x%d, %%%d;" % (acc, xi, acc))
+                if PAIR == 1:
+                    a("fma.rn.f32 %%%d, wcur, x%d, %%%d;" % (acc, xi, acc))
+                else:
+                    a("fma.rn.f32x2 a%d, ww, x%d, a%d;" % (acc, xi, acc))
         L.extend(adv)
     a("HLOAD:")
+    a(fetch)
     # wcur = byte offset of the input-channel plane inside the staged chunk; %NACC+1 = lane base address (shared,
     # bytes); %NACC+2 = row pitch in bytes
-    a("add.u32 ad0, %%%d, wcur;" % (NACC + 1))
+    a("add.u32 ad0, %%%d, wcur;" % (NOPS + 1))
     for r in range(1, PR):
-        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NACC + 2))
+        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
     for r in range(PR):
-        for v in range(PCV):
-            b = r * XW + v * 4
-            a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d+%d];" % (b, b + 1, b + 2, b + 3, r, v * 16))
+        for (po, cnt) in loads:
+            b = r * XW + po
+            byte = po * 4 * PAIR
+            if PAIR == 1 and cnt == 4:
+                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d+%d];" % (b, b + 1, b + 2, b + 3, r, byte))
+            elif PAIR == 1:
+                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d+%d];" % (b, b + 1, r, byte))
+            elif cnt == 2:
+                a("ld.shared.v2.b64 {x%d, x%d}, [ad%d+%d];" % (b, b + 1, r, byte))
+            else:
+                a("ld.shared.b64 x%d, [ad%d+%d];" % (b, r, byte))
     L.extend(adv)
     a("HEND:")
+    if PAIR == 2:
+        for i in range(NACC):
+            a("mov.b64 {%%%d, %%%d}, a%d;" % (2 * i, 2 * i + 1, i))
     a("}")
     body = "\n".join('      "%s\\n\\t"' % s for s in L)
-    ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NACC))
-    name = "o%d_y%d_x%d_k%dx%d_s%d_w%d" % (OT, TY, TX, KH, KW, S, NCW)
+    ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
+    name = "o%d_y%d_x%d_k%dx%d_s%d_p%d_w%d" % (OT, TY, TX, KH, KW, S, PAIR, NCW)
     src = []
-    src.append("// ---- variant %s: %d accumulators, %d patch registers, %d handlers ----" % (name, NACC, NX, NC + 2))
-    src.append("template <> struct Interp<%d, %d, %d, %d, %d, %d> {" % (OT, TY, TX, KH, KW, S))
-    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d;" % (NACC, NC, PR, PC, XW))
+    src.append("// ---- variant %s: %d accumulator registers%s, %d patch registers, %d handlers ----"
+               % (name, NACC, "" if PAIR == 1 else " (64-bit pairs)", NX, NC + 2))
+    src.append("template <> struct Interp<%d, %d, %d, %d, %d, %d, %d> {" % (OT, TY, TX, KH, KW, S, PAIR))
+    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d;  // NACC fp32 accumulators"
+               % (NOPS, NC, PR, PC, XW))
     src.append("  static constexpr int NCW = %d, NLW = %d;" % (NCW, NLW))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
-    src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], const void *prog, unsigned lane_base,"
-               % NACC)
+    src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base,"
+               % NOPS)
     src.append("                                             unsigned pitch_bytes) {")
     src.append("    asm volatile(")
     src.append(body)
     src.append("      : %s" % ops_out)
-    src.append('      : "l"(prog), "r"(lane_base), "r"(pitch_bytes)')
+    src.append('      : "r"(prog), "r"(lane_base), "r"(pitch_bytes)')
     src.append('      : "memory");')
     src.append("  }")
     src.append("};")
@@ -104,18 +160,18 @@ def gen_variant(OT, TY, TX, KH, KW, S, NCW, NLW):
 def main():
     os.makedirs(OUTDIR, exist_ok=True)
     head = ["// GENERATED by tools/gen_interp.py -- do not edit.  Inline-PTX threaded-code interpreter for one tile shape.",
-            "// Record stream: 8-byte records {u32 payload, u32 handler}; handler < NC: FMA (payload = fp32 weight),",
-            "// handler == NC: LOAD patch (payload = byte offset of the channel plane), NC+1: end of segment.",
+            "// Record stream (shared memory): 8-byte records {u32 payload, u32 handler}; handler < NC: FMA (payload =",
+            "// fp32 weight), handler == NC: LOAD patch (payload = byte offset of the channel plane), NC+1: end of segment.",
             "#pragma once",
-            "template <int OT, int TY, int TX, int KH, int KW, int S> struct Interp;"]
+            "template <int OT, int TY, int TX, int KH, int KW, int S, int PAIR> struct Interp;"]
     for i, v in enumerate(VARIANTS):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
-        txt = "\n".join(head + [gen_variant(*v), "#define ESCORT_VARIANT_ARGS %d, %d, %d, %d, %d, %d" % v[:6]]) + "\n"
+        txt = "\n".join(head + [gen_variant(*v), "#define ESCORT_VARIANT_ARGS %d, %d, %d, %d, %d, %d, %d" % v[:7]]) + "\n"
         if not os.path.exists(path) or open(path).read() != txt:
             open(path, "w").write(txt)
     lst = os.path.join(OUTDIR, "variant_list.inc")
     txt = "// GENERATED by tools/gen_interp.py\n#define ESCORT_NUM_VARIANTS %d\n#define ESCORT_VARIANT_LIST(X) \\\n" % len(VARIANTS)
-    txt += " \\\n".join("  X(%d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + v) for i, v in enumerate(VARIANTS)) + "\n"
+    txt += " \\\n".join("  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + v) for i, v in enumerate(VARIANTS)) + "\n"
     if not os.path.exists(lst) or open(lst).read() != txt:
         open(lst, "w").write(txt)
     print("generated %d variants in %s" % (len(VARIANTS), OUTDIR))

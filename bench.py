@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the Escort direct-sparse-convolution hot path on B200 (contract: see DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload alexnet|googlenet|resnet50]
+
+One "step" = one forward pass of every sparse conv layer of the workload over one batch of synthetic input
+(BASELINE.json configs[1] by default: AlexNet conv2..conv5 pruned to 85-88 %, batch 256 per GPU).  With N > 1 the
+batch is sharded: every rank runs its own 256 images, no data-path collective (inference), "scaling": "weak".
+
+Our arm prints ONE JSON line with
+  value     images/s with the inputs resident in HBM (CUDA events, max over ranks),
+  e2e       images/s through the C-ABI with HOST buffers: pinned-host -> device copies of every layer input that
+            comes from outside the path and device -> host copies of its outputs inside the timed region,
+  roofline  the dominant kernel against max(nnz-FLOPs / FP32-FMA peak, compulsory bytes / HBM bandwidth),
+  cpu_baseline  the reference's own CPU direct sparse conv (oracle/_ref, AVX2 + OpenMP) timed on this host.
+`--impl reference` times that CPU path alone (rank 0 only) and prints the same line with "impl": "reference".
+
+Only the cpu_baseline / --impl reference legs touch oracle/; the product path is the CUDA library through ctypes.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sparse_conv_images_per_sec"
+UNIT = "images/s"
+
+
+def _peaks():
+    """HBM peak from the driver-written MEASURED_PEAKS.json, else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def _workload(name):
+    from caffe_escoin_b200 import workloads as wl
+    specs = {"alexnet": wl.ALEXNET, "googlenet": wl.GOOGLENET, "resnet50": wl.RESNET50, "lenet": wl.LENET}[name]
+    label = {"alexnet": "alexnet_conv2-conv5_pruned85-88_fwd_b256",
+             "googlenet": "googlenet_v1_3x3_5x5_pruned75_fwd_b128",
+             "resnet50": "resnet50_branch2b_3x3_pruned70_fwd_b256",
+             "lenet": "lenet5_conv1-2_pruned80_fwd_b64"}[name]
+    return specs, label
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            return None
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        # samples under load = the upper half (the sampler also sees the idle edges of the region)
+        busy = sorted(sm)[len(sm) // 2:]
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU kernels (oracle/_ref), all host threads
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(specs, sample, steps, warmup):
+    """Times `steps` passes of the workload's layers over `sample` images with the reference's CPU direct sparse
+    conv (sconv_unit_stride<W,K> where the reference has the specialisation, else caffe_cpu_sconv_default;
+    pad copy included; omp-parallel over images).  Returns (images_per_s, ms_per_step, threads, kind)."""
+    from caffe_escoin_b200 import workloads as wl
+    from oracle import pyoracle as po
+    po.build()
+    kind = "reference" if po.have_ref() else "port"
+    threads = po.ref().ref_max_threads() if po.have_ref() else po.lib().oracle_max_threads()
+    layers = []
+    for li, spec in enumerate(specs):
+        n = min(sample, spec.N)
+        d = wl.make_layer_data(spec, li, N=n)
+        g = po.Geom(n, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+        csr = po.weight_align(d["w"], g)
+        layers.append((spec, g, csr, d))
+    n = min(sample, specs[0].N)
+
+    def step():
+        for spec, g, csr, d in layers:
+            if kind == "reference":
+                po.ref_conv_forward(d["x"], csr, g, d["bias"], relu=True, threads=threads)
+            else:
+                po.conv_forward(d["x"], csr, g, d["bias"], relu=True, threads=threads)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return n * steps / dt, dt / steps * 1e3, int(threads), kind
+
+
+def run_reference(args, specs, label):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = specs[0].N if args.sample <= 0 else args.sample
+    # keep the whole run within a few minutes whatever the host: calibrate on a small slice first
+    ips, _, threads, kind = cpu_reference_run(specs, min(16, sample), 1, 1)
+    budget_s = 120.0
+    if sample / ips * (args.steps + args.warmup) > budget_s:
+        sample = max(8, int(budget_s * ips / (args.steps + args.warmup)))
+    ips, ms, threads, kind = cpu_reference_run(specs, sample, args.steps, args.warmup)
+    desc = "%d of %d images per step through all %d layers, %s" % (
+        sample, specs[0].N, len(specs),
+        "reference AVX2 sconv_unit_stride / caffe_cpu_sconv_default + OpenMP over images" if kind == "reference"
+        else "oracle C port + OpenMP over images")
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": label, "batch_per_step": sample, "device": "host CPU"},
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args, specs, label):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as ge
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the sparse-conv path has no CPU fallback "
+                         "(use --impl reference for the CPU reference arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not os.path.exists(os.path.join(ROOT, "caffe_escoin_b200", "libescort_b200.so")):
+        if rank == 0:
+            ge.build()
+        if world > 1:
+            dist.barrier()
+    from caffe_escoin_b200 import capi, workloads as wl
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- FP32 FMA peak, measured live (not in MEASURED_PEAKS.json) ----
+    fp32_peaks = {}
+    for v, name in ((0, "ffma_shared_operand"), (1, "ffma2_packed"), (2, "ffma_3reg")):
+        fp32_peaks[name] = capi.measure_fp32_peak(v, 8192)[0]
+    fp32_peak = max(fp32_peaks.values())
+    hbm_peak, hbm_src = _peaks()
+
+    # ---- set-up (untimed): weights -> CSR through the C ABI (WeightAlign) -> plan, autotuned at the batch size ----
+    layers = []
+    host_in, host_out = [], []
+    for li, spec in enumerate(specs):
+        d = wl.make_layer_data(spec, li)
+        geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
+        csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)
+        plan = capi.Plan(geom, csr)
+        if args.variant is None:
+            plan.autotune(spec.N)
+        else:
+            plan.set_variant(args.variant)
+        x = torch.from_numpy(d["x"]).cuda()
+        b = torch.from_numpy(d["bias"]).cuda() if d["bias"] is not None else None
+        y = torch.empty((spec.N, spec.Cout, plan.Ho, plan.Wo), device="cuda")
+        flops, byts = wl.alg_work(spec, plan.nnz)
+        layers.append(dict(spec=spec, plan=plan, x=x, b=b, y=y, flops=flops, bytes=byts, csr=csr))
+        host_in.append(torch.from_numpy(d["x"]).pin_memory())
+        host_out.append(torch.empty(y.shape, dtype=torch.float32).pin_memory())
+    N = specs[0].N
+    nl = len(layers)
+
+    def step(events=None):
+        for i, L in enumerate(layers):
+            if events is not None:
+                events[i][0].record()
+            L["plan"].forward(L["x"], L["b"], relu=True, top=L["y"])
+            if events is not None:
+                events[i][1].record()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
+           for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for s in range(args.steps):
+        step(evs[s])
+    t1.record()
+    barrier()
+    ms_total = t0.elapsed_time(t1)
+    clocks = sampler.stop() if sampler else None
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * N * args.steps / (ms_total * 1e-3)
+    layer_ms = [float(np.mean([evs[s][i][0].elapsed_time(evs[s][i][1]) for s in range(args.steps)])) for i in range(nl)]
+
+    # ---- e2e: host buffers in, host buffers out, copies inside the timed region, chunk-pipelined over streams ----
+    nchunk = 4 if N % 4 == 0 else 1
+    cs = N // nchunk
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    h2d = sum(h.numel() * 4 for h in host_in)
+    d2h = sum(h.numel() * 4 for h in host_out)
+
+    def e2e_step():
+        k = 0
+        for i, L in enumerate(layers):
+            for c in range(nchunk):
+                st = streams[k % len(streams)]
+                k += 1
+                with torch.cuda.stream(st):
+                    sl = slice(c * cs, (c + 1) * cs)
+                    L["x"][sl].copy_(host_in[i][sl], non_blocking=True)
+                    L["plan"].forward(L["x"][sl], L["b"], relu=True, top=L["y"][sl], stream=st)
+                    host_out[i][sl].copy_(L["y"][sl], non_blocking=True)
+        for st in streams:
+            st.synchronize()
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    w0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - w0
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * N * args.steps / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (largest share of the step) ----
+    dom = int(np.argmax(layer_ms))
+    L = layers[dom]
+    t_meas = layer_ms[dom] * 1e-3
+    t_fma = L["flops"] / (fp32_peak * 1e12)
+    t_hbm = L["bytes"] / (hbm_peak * 1e9)
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(L["spec"].name, {}).get(L["plan"].kernel_name)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "fp32_fma" if t_fma >= t_hbm else "hbm", "kernel": L["plan"].kernel_name,
+                "layer": L["spec"].name, "achieved": L["flops"] / t_meas / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": max(t_fma, t_hbm) / t_meas,
+                "peak_source": "FP32 FMA: measured live by escort_measure_fp32_peak (best of FFMA / FFMA2 "
+                               "register-resident loops); HBM: " + hbm_src,
+                "alg_flops_per_launch": L["flops"], "alg_bytes_per_launch": L["bytes"],
+                "launch_ms": layer_ms[dom], "hbm_achieved_gbs": L["bytes"] / t_meas / 1e9, "hbm_peak_gbs": hbm_peak,
+                "traffic": traffic, "fp32_peaks_tflops": fp32_peaks}
+    per_layer = []
+    for i, Lr in enumerate(layers):
+        tf, th = Lr["flops"] / (fp32_peak * 1e12), Lr["bytes"] / (hbm_peak * 1e9)
+        per_layer.append({"layer": Lr["spec"].name, "kernel": Lr["plan"].kernel_name, "ms": layer_ms[i],
+                          "images_per_s": N / (layer_ms[i] * 1e-3), "tflops": Lr["flops"] / layer_ms[i] / 1e9,
+                          "roofline_frac": max(tf, th) / (layer_ms[i] * 1e-3), "nnz": int(Lr["plan"].nnz)})
+
+    # ---- cpu_baseline (N = 1 only): the reference's CPU path on this host, bounded sample ----
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            sample = min(N, 64)
+            ips, ms, threads, kind = cpu_reference_run(specs, sample, 3, 1)
+            cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
+                   "sample": "%d of %d images x 3 steps through all %d layers (reference CPU direct sconv, "
+                             "OpenMP over images)" % (sample, N, nl)}
+        except Exception as e:  # the baseline is reported, never required
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": label, "batch_per_gpu": N, "global_batch": N * world, "parallelism": "batch-shard x%d, "
+                       "no data-path collective" % world, "epilogue": "bias+ReLU fused",
+                       "l2": "inputs+outputs of one step (%.0f MB) exceed the 126 MB L2, so every step re-reads HBM"
+                             % (sum(Lr["bytes"] for Lr in layers) / 1e6)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "how": "pinned host -> device, C-ABI forward, device -> pinned host; %d-image chunks over 2 streams"
+                           % cs},
+            "gpu_launches": nl * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+            "layers": per_layer}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="alexnet", choices=["alexnet", "googlenet", "resnet50", "lenet"])
+    ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = the full batch)")
+    ap.add_argument("--variant", type=int, default=None, help="force a forward variant instead of autotuning")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    specs, label = _workload(args.workload)
+    if args.impl == "reference":
+        run_reference(args, specs, label)
+    else:
+        run_ours(args, specs, label)
+
+
+if __name__ == "__main__":
+    main()

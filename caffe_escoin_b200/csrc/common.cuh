@@ -77,4 +77,6 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
                  cudaStream_t stream);
 int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream);
 const char *tile_kernel_name(const TilePlan *tp);
+int tile_num_variants();
+bool tile_variant_applies(const escort_plan *plan, int variant);  // variant = 1-based index
 }  // namespace escort

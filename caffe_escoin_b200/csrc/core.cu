@@ -465,6 +465,57 @@ extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
   return 0;
 }
 
+// Plan-time selection of the forward variant by measurement (the cuDNN "find" idiom): every variant that
+// supports the geometry is built and timed on a zero-filled scratch batch of `num` images on `stream`; the
+// fastest is kept.  Called by the host layer once after WeightAlign; synchronises the stream.
+extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");
+  const escort_geom &g = p->g;
+  const size_t in_elems = (size_t)num * g.channels * g.height * g.width;
+  const size_t out_elems = (size_t)num * g.num_output * p->Ho * p->Wo;
+  float *x = nullptr, *y = nullptr;
+  ESCORT_CUDA(cudaMalloc((void **)&x, in_elems * sizeof(float)));
+  cudaError_t e = cudaMalloc((void **)&y, out_elems * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(x);
+    return cuda_fail(e, "cudaMalloc(autotune scratch)", __FILE__, __LINE__);
+  }
+  cudaMemsetAsync(x, 0, in_elems * sizeof(float), stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int best_v = 0;
+  float best_ms = 1e30f;
+  const int nvar = tile_num_variants();
+  for (int v = 0; v <= nvar; ++v) {
+    if (v > 0 && !tile_variant_applies(p, v)) continue;
+    if (escort_plan_set_variant(p, v) != 0) continue;
+    if (v > 0 && !p->tile) continue;
+    float ms_best = 1e30f;
+    bool ok = true;
+    for (int it = 0; it < 3 && ok; ++it) {
+      cudaEventRecord(e0, stream);
+      ok = escort_sconv_forward(p, num, x, nullptr, 0, y, stream) == 0;
+      cudaEventRecord(e1, stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (it > 0 && ms < ms_best) ms_best = ms;
+    }
+    if (ok && ms_best < best_ms) {
+      best_ms = ms_best;
+      best_v = v;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(x);
+  cudaFree(y);
+  cudaGetLastError();
+  return escort_plan_set_variant(p, best_v);
+}
+
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,
                                     float *top, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

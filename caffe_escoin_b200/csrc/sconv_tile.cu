@@ -99,6 +99,14 @@ void tile_plan_free(TilePlan *tp) {
 }
 
 const char *tile_kernel_name(const TilePlan *tp) { return tp->name; }
+int tile_num_variants() { return kNumVariants; }
+bool tile_variant_applies(const escort_plan *plan, int variant) {
+  if (variant < 1 || variant > kNumVariants) return false;
+  const VariantDesc &v = kVariants[variant - 1];
+  const escort_geom &g = plan->g;
+  return v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h && g.stride_h == g.stride_w &&
+         g.dilation_h == 1 && g.dilation_w == 1;
+}
 
 // Pick the default variant for a geometry (auto mode); returns -1 if the tile kernel does not apply.
 static int choose_variant(const escort_geom &g, double density) {
@@ -385,7 +393,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
   }
   pr.lanes = tp->d_lanes; pr.oc_list = tp->d_oc_list; pr.prog = tp->d_prog; pr.rtab = tp->d_rtab; pr.dst_off = tp->d_dst_off;
-  e = cudaFuncSetAttribute(V.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tp->smem_bytes);
+  // the attribute belongs to the kernel, not the plan: several plans share a variant, so always raise it to the
+  // device's opt-in maximum instead of this plan's own size
+  e = cudaFuncSetAttribute(V.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
   if (e != cudaSuccess) {
     tile_plan_free(tp);
     return cuda_fail(e, "cudaFuncSetAttribute(smem)", __FILE__, __LINE__);

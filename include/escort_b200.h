@@ -105,6 +105,11 @@ ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int bufl
 /* tuning knob for tests/bench: force a forward variant (-1 auto, 0 generic, >0 tile-interpreter variants) */
 ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
 
+/* measure every forward variant that supports the geometry on a scratch batch of `num` images and keep the
+ * fastest (plan-time selection, like cuDNN's find); synchronises `stream`.  Optional: without it the plan
+ * uses a static default. */
+ESCORT_API int escort_plan_autotune(escort_plan *plan, int num, escort_stream_t stream);
+
 /* ---- a5-a9: native forward ---------------------------------------------------------------------------------
  * Replaces the whole per-image sequence of ConvolutionLayer::Forward_gpu in SCONV / SCONV_PAR mode
  * (src/caffe/layers/conv_layer.cu:15-26) = forward_gpu_sconv[_par] (base_conv_layer.cpp:749-848:

@@ -23,7 +23,7 @@ class Geom(C.Structure):
 
 EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
            "escort_plan_destroy", "escort_plan_nnz", "escort_plan_kernel_name", "escort_plan_describe",
-           "escort_plan_set_variant", "escort_plan_autotune",
+           "escort_plan_set_variant", "escort_plan_set_config", "escort_plan_autotune",
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_measure_fp32_peak",
            "escort_last_error", "escort_version"]
@@ -36,6 +36,7 @@ lib.escort_plan_nnz.restype = C.c_long
 lib.escort_plan_nnz.argtypes = [C.c_void_p]
 lib.escort_plan_destroy.argtypes = [C.c_void_p]
 lib.escort_plan_set_variant.argtypes = [C.c_void_p, C.c_int]
+lib.escort_plan_set_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.escort_plan_autotune.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 
@@ -149,6 +150,9 @@ class Plan:
 
     def set_variant(self, v):
         _check(lib.escort_plan_set_variant(self.h, int(v)), "escort_plan_set_variant")
+
+    def set_config(self, v, rank):
+        _check(lib.escort_plan_set_config(self.h, int(v), int(rank)), "escort_plan_set_config")
 
     def autotune(self, num, stream=None):
         _check(lib.escort_plan_autotune(self.h, int(num), _stream(stream)), "escort_plan_autotune")

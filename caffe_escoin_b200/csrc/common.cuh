@@ -52,6 +52,7 @@ struct escort_plan {
   int device;
   long nnz;
   int variant;  // -1 auto
+  int layout_rank;  // which of the tile planner's layout candidates (0 = best heuristic score)
   // ---- generic forward: row-major (global rows) ----
   int *d_rowptr;    // num_output + 1
   int4 *d_meta;     // nnz: {in_off, dy, dx, val bits}; in_off = ic*H*W + dy*W + dx  (may be negative)

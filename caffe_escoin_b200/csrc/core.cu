@@ -379,6 +379,7 @@ extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, co
   p->Wo = Wo;
   p->nnz = nnz;
   p->variant = -1;
+  p->layout_rank = 0;
   p->host_nz = nzs;
   cudaGetDevice(&p->device);
 
@@ -448,7 +449,12 @@ extern "C" const char *escort_plan_kernel_name(const escort_plan *p) {
 }
 
 extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
-  ESCORT_REQUIRE(p, "escort_plan_set_variant: null plan");
+  return escort_plan_set_config(p, variant, 0);
+}
+
+extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_rank) {
+  ESCORT_REQUIRE(p && layout_rank >= 0, "escort_plan_set_config: bad arguments");
+  p->layout_rank = layout_rank;
   if (p->tile) {
     tile_plan_free(p->tile);
     p->tile = nullptr;
@@ -459,7 +465,7 @@ extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
   if (rc) return rc;
   ESCORT_CUDA(cudaStreamSynchronize(0));
   if (variant > 0 && !p->tile) {
-    set_last_error("escort_plan_set_variant: geometry not supported by the requested tile variant");
+    set_last_error("escort_plan_set_config: geometry / layout candidate not supported by the requested tile variant");
     return ESCORT_EINVAL;
   }
   return 0;
@@ -488,24 +494,28 @@ extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t str
   int best_v = 0;
   float best_ms = 1e30f;
   const int nvar = tile_num_variants();
+  int best_rank = 0;
   for (int v = 0; v <= nvar; ++v) {
     if (v > 0 && !tile_variant_applies(p, v)) continue;
-    if (escort_plan_set_variant(p, v) != 0) continue;
-    if (v > 0 && !p->tile) continue;
-    float ms_best = 1e30f;
-    bool ok = true;
-    for (int it = 0; it < 3 && ok; ++it) {
-      cudaEventRecord(e0, stream);
-      ok = escort_sconv_forward(p, num, x, nullptr, 0, y, stream) == 0;
-      cudaEventRecord(e1, stream);
-      if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
-      float ms = 0.f;
-      cudaEventElapsedTime(&ms, e0, e1);
-      if (it > 0 && ms < ms_best) ms_best = ms;
-    }
-    if (ok && ms_best < best_ms) {
-      best_ms = ms_best;
-      best_v = v;
+    for (int rank = 0; rank < (v == 0 ? 1 : 4); ++rank) {
+      if (escort_plan_set_config(p, v, rank) != 0) break;  // no such layout candidate
+      if (v > 0 && !p->tile) break;
+      float ms_best = 1e30f;
+      bool ok = true;
+      for (int it = 0; it < 3 && ok; ++it) {
+        cudaEventRecord(e0, stream);
+        ok = escort_sconv_forward(p, num, x, nullptr, 0, y, stream) == 0;
+        cudaEventRecord(e1, stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (it > 0 && ms < ms_best) ms_best = ms;
+      }
+      if (ok && ms_best < best_ms) {
+        best_ms = ms_best;
+        best_v = v;
+        best_rank = rank;
+      }
     }
   }
   cudaEventDestroy(e0);
@@ -513,7 +523,7 @@ extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t str
   cudaFree(x);
   cudaFree(y);
   cudaGetLastError();
-  return escort_plan_set_variant(p, best_v);
+  return escort_plan_set_config(p, best_v, best_rank);
 }
 
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,

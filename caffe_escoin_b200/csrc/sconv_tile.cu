@@ -22,10 +22,12 @@
 #include <cstring>
 #include <numeric>
 
+#include <cuda.h>
+
 #include "common.cuh"
 #include "generated/variant_list.inc"
 #define ESCORT_TILE_HOST_ONLY
-template <int OT, int TY, int TX, int KH, int KW, int S, int PAIR> struct Interp;  // device side: tile_variant.cu
+template <int VID> struct Interp;  // device side: tile_variant.cu
 #include "tile_kernel.cuh"
 
 namespace escort {
@@ -34,14 +36,16 @@ namespace escort {
 // variant table
 // ------------------------------------------------------------------------------------------------------
 struct VariantDesc {
-  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW;
+  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW;
   const char *name;
   const void *kernel;
+  const void *bench;
 };
 
 // one translation unit per variant (tile_variant.cu compiled with -DESCORT_VARIANT_ID=k) exports these
-#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW) \
+#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW) \
   const void *tile_variant_kernel_##ID();                         \
+  const void *tile_variant_bench_##ID();                          \
   const char *tile_variant_name_##ID();
 ESCORT_VARIANT_LIST(ESCORT_VARIANT_DECL)
 static constexpr int kNumVariants = ESCORT_NUM_VARIANTS;
@@ -49,8 +53,8 @@ static const VariantDesc *variants() {
   static VariantDesc tab[kNumVariants];
   static bool init = false;
   if (!init) {
-#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW) \
-  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, tile_variant_name_##ID(), tile_variant_kernel_##ID()};
+#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW) \
+  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID()};
     ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
     init = true;
   }
@@ -93,7 +97,6 @@ void tile_plan_free(TilePlan *tp) {
   cudaFree(tp->d_oc_list);
   cudaFree(tp->d_prog);
   cudaFree(tp->d_rtab);
-  cudaFree(tp->d_dst_off);
   cudaFree(tp->d_prog_pos);
   delete tp;
 }
@@ -118,6 +121,25 @@ static int choose_variant(const escort_geom &g, double density) {
   }
   (void)density;
   return best;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*TmaEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encoder() {
+  static TmaEncodeFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (TmaEncodeFn)p;
+    cudaGetLastError();
+  }
+  return fn;
 }
 
 namespace {
@@ -148,6 +170,7 @@ std::vector<Slot> enumerate_slots(int GP, int BR, int PX, int order) {
 }  // namespace
 
 int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
+  const int layout_rank = plan->layout_rank;
   plan->tile = nullptr;
   const escort_geom &g = plan->g;
   if (g.dilation_h != 1 || g.dilation_w != 1 || g.stride_h != g.stride_w) return 0;
@@ -159,7 +182,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     vidx = variant - 1;
     if (vidx >= kNumVariants) return 0;
     const VariantDesc &v = kVariants[vidx];
-    if (v.KH != g.kernel_h || v.KW != g.kernel_w || v.S != g.stride_h) return 0;
+    if (!tile_variant_applies(plan, variant)) return 0;
   } else {
     vidx = choose_variant(g, density);
     if (vidx < 0) return 0;
@@ -170,21 +193,34 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int Ho = plan->Ho, Wo = plan->Wo;
   const int PY = ceil_div(Ho, TY), PX = ceil_div(Wo, TX);
   const int per_vec = 4 / PAIR;
-  const int PC = (TX - 1) * S + KW, XW = ceil_div(PC, per_vec) * per_vec;
-  // every lane's vector over-read stays inside its row; the pitch keeps 16-byte alignment of every row start
-  const int Pmin = ceil_div(std::max((PX - 1) * TX * S + XW, g.width + g.pad_w), per_vec) * per_vec;
+  const int PC = (TX - 1) * S + KW;
+  // columns the patch-aligned load plan touches (128-bit loads with a 64-bit tail; PAIR 2: exactly PC positions)
+  const int XW = PAIR == 2 ? PC : (PC % 4 == 0 ? PC : (PC % 4 <= 2 ? PC - PC % 4 + 2 : PC - PC % 4 + 4));
+  // TMA staging (cp.async.bulk.tensor with out-of-bounds zero fill = the halo) needs 16-byte global strides and a
+  // 16-byte aligned innermost start coordinate, hence the aligned-body row layout
+  const bool use_tma = PAIR == 1 && g.width % 4 == 0 && g.pad_w == (KW - 1) / 2 && tma_encoder() != nullptr &&
+                       !getenv("ESCORT_NO_TMA");
+  // PAIR 1: data column 0 sits on a 16-byte boundary, HL halo columns to its left (aligned-body layout: TMA and the
+  // lanes' 128-bit loads both need it); PAIR 2: the halo is exactly pad_w positions wide.
+  const int PADL = use_tma ? (KW - 1) / 2 : 0;
+  const int HL = use_tma ? (g.pad_w > 0 ? 4 : 0) : g.pad_w;
+  const int lane_col0 = use_tma ? HL : 0;
+  // every lane's reads stay inside its row; the pitch keeps 16-byte alignment of every row start
+  const int Pmin = ceil_div(std::max(lane_col0 + (PX - 1) * TX * S + (use_tma ? PC - PADL : XW), HL + g.width + g.pad_w), per_vec) * per_vec;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
   if (max_smem <= 0) max_smem = 227 * 1024;
   if (num_sms <= 0) num_sms = 148;
-  const int tab_bytes = ceil_div(std::max(1, ((TY * PY - 1) * S + KH) * g.width) * 2, 128) * 128;
+  const int tab_bytes = 0;
   const long smem_budget = (long)max_smem - kBarBytes - 256;
   const int nblk = ceil_div(Mg, OT);
 
-  // ---- choose (WP, BR, G, pitch, skew, lane order): lane utilisation first, then bank conflicts / reuse ----
-  Layout best = {0, 0, 0, 0, 0, 0, 0, -1.0};
+  // ---- choose (WP, BR, G, pitch, slot residue, lane order): lane utilisation first, then bank conflicts / reuse.
+  // "skew" = image-slot stride modulo 32 floats (the bank offset between the image slots of a stage); TMA
+  // destinations are 128-byte aligned, so it is 0 there ----
+  std::vector<Layout> cands;  // one per (WP, BR), best pitch / residue / lane order each
   for (int WP = 1; WP <= NCW; ++WP) {
     if (NCW % WP) continue;
     const int lanes = WP * 32;
@@ -197,52 +233,56 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
       const int GP = std::min(lanes / per_slot, 16);
       const int G = GP * PAIR;
       const int R = (BR * TY - 1) * S + KH;
-      if ((long)R * g.width * 2 > tab_bytes) continue;
       const int nslots = GP * per_slot;
       const double util = (double)nslots / lanes * ((double)Ho * Wo / ((double)PY * TY * PX * TX));
       const double band_waste = (double)PY / (nb * BR);
       const double wo_eff = (double)std::min(WO, nblk) / WO;
       const double halo = (double)(BR * TY * S) / R;
       double base_score = util * band_waste * wo_eff * (0.85 + 0.15 * halo) * (1.0 + 0.02 * std::log2((double)WO));
-      if (base_score < best.score * 0.98) continue;
       // pitch / skew / lane order with the fewest LDS.128 wavefronts
       int bP = Pmin, bskew = 0, border = 0, bcost = 1 << 30;
       const int orders[4] = {0, 4, 2, 1};
       for (int oi = 0; oi < 4; ++oi) {
         const std::vector<Slot> slots = enumerate_slots(GP, BR, PX, orders[oi]);
         for (int P = Pmin; P <= Pmin + 8 * per_vec; P += per_vec) {
-          for (int skew = 0; skew <= 4; skew += 4) {
-            const int plane_f = R * P * PAIR + skew;
+          for (int skew = 0; skew <= (use_tma ? 0 : 28); skew += 4) {
             int wsum = 0;
             for (int w = 0; w < WP; ++w) {
               std::vector<unsigned> addr;
               for (int l = 0; l < 32 && w * 32 + l < nslots; ++l) {
                 const Slot &sl = slots[w * 32 + l];
-                addr.push_back((unsigned)((sl.gs * plane_f + (sl.pyb * TY * S * P + sl.px * TX * S) * PAIR) * 4));
+                addr.push_back((unsigned)((sl.gs * (skew + 8192) + (sl.pyb * TY * S * P + sl.px * TX * S) * PAIR) * 4));  // distinct slots, same residue
               }
               if (!addr.empty()) wsum += lds128_wavefronts(addr);
             }
-            const int cost = wsum * 256 + (P - Pmin) * 8 + skew + oi;
+            const int cost = wsum * 4096 + (P - Pmin) * 64 + skew + oi;
             if (cost < bcost) { bcost = cost; bP = P; bskew = skew; border = orders[oi]; }
           }
         }
       }
-      const long plane_bytes = ((long)R * bP * PAIR + bskew) * 4 * GP;
+      const long plane_bytes = ((long)R * bP * PAIR + 32) * 4 * GP;
       if (3 * plane_bytes > smem_budget - tab_bytes) continue;  // at least 1 channel x 3 stages (program space extra)
       const int ideal = WP * 4;  // 4 wavefronts per LDS.128 per warp is conflict free
-      const double conflict = (double)ideal / std::max(ideal, bcost / 256);
-      const double score = base_score * (0.6 + 0.4 * conflict);
-      if (score > best.score) best = {WP, G, BR, bP, R, bskew, border, score};
+      const double conflict = (double)ideal / std::max(ideal, bcost / 4096);
+      // a stage should hold several channels (per-chunk hand-shake and interpreter entry/exit are fixed costs) and a
+      // unit several channel blocks (every block re-reads the staged input)
+      const long ci_est = std::min<long>((smem_budget - tab_bytes) / (3 * plane_bytes), (long)Cg);
+      const double chunk_f = std::min(1.0, 0.55 + 0.075 * (double)ci_est);
+      const double reuse_f = 1.0 - 0.35 / (double)WO;
+      const double score = base_score * (0.6 + 0.4 * conflict) * chunk_f * reuse_f;
+      cands.push_back({WP, G, BR, bP, R, bskew, border, score});
     }
   }
-  if (best.score < 0) return 0;
+  std::stable_sort(cands.begin(), cands.end(), [](const Layout &a, const Layout &b) { return a.score > b.score; });
+  if (layout_rank < 0 || layout_rank >= (int)cands.size()) return 0;
+  const Layout best = cands[layout_rank];  // rank 0 = the heuristic's favourite; autotune also times the runners-up
   const int WP = best.WP, G = best.G, GP = G / PAIR, BR = best.BR, P = best.P, R = best.R;
   const int WO = NCW / WP;
   const int nbands = ceil_div(PY, BR);
   const int ogroups = ceil_div(nblk, WO);
   const int per_slot = BR * PX;
   const int nslots = GP * per_slot;
-  const int plane_f = R * P * PAIR + best.skew;
+  const int plane_f = R * P * PAIR;
   const int hdr_bytes = ceil_div(WO * 4, 16) * 16;
 
   // ---- nnz-balanced channel blocks: rows sorted by nnz (desc), dealt in snake order ----
@@ -276,11 +316,15 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   std::vector<uint4> prog;
   std::vector<int2> rtab;
   std::vector<int> prog_pos;
-  int nchunks = 0, NS = 0, in_bytes = 0, stage_bytes = 0, max_region16 = 0;
+  int nchunks = 0, NS = 0, in_bytes = 0, stage_bytes = 0, max_region16 = 0, slot_f = 0;
   for (int attempt = 0; attempt < 8; ++attempt) {
     nchunks = ceil_div(Cg, CI);
     CI = ceil_div(Cg, nchunks);  // even out the chunks
-    in_bytes = (int)(plane_bytes * CI);
+    // image slots are the outer dimension of a stage ([slot][channel][row][col]); the slot stride keeps the bank
+    // offset between slots that the layout search assumed (TMA destinations must be 128-byte aligned instead)
+    slot_f = CI * plane_f;
+    while ((slot_f - best.skew) % 32) slot_f += 4;
+    in_bytes = GP * slot_f * 4;
     std::vector<std::vector<Rec>> buckets((size_t)g.group * nblk * nchunks);
     for (size_t j = 0; j < nz.size(); ++j) {
       const Nz &z = nz[j];
@@ -307,24 +351,38 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
                 if (a.kw != b.kw) return a.kw < b.kw;
                 return a.o < b.o;
               });
+              // record i = {payload_i, handler_(i+2)}; a header {handler_0, handler_1} opens the segment
+              std::vector<std::pair<unsigned, unsigned>> seq;  // (payload, own handler)
+              std::vector<int> seq_src;
               int cur_ic = -1;
               for (const Rec &r : v) {
                 if (r.ic != cur_ic) {
                   cur_ic = r.ic;
-                  words.push_back((unsigned)((r.ic - c * CI) * (long)GP * plane_f * 4));
-                  words.push_back((unsigned)NC);
+                  seq.push_back({(unsigned)((r.ic - c * CI) * (long)plane_f * 4), (unsigned)(use_tma ? NC + 1 : NC)});
+                  seq_src.push_back(-1);
                 }
-                prog_pos[r.src] = (int)(words.size() / 2);
-                words.push_back(__builtin_bit_cast(unsigned, r.val));
-                words.push_back((unsigned)((r.o * KH + r.kh) * KW + r.kw));
+                seq.push_back({__builtin_bit_cast(unsigned, r.val), (unsigned)((r.o * KH + r.kh) * KW + r.kw)});
+                seq_src.push_back(r.src);
               }
+              seq.push_back({0u, (unsigned)(NC + 2)});  // end of segment
+              seq_src.push_back(-1);
+              words.push_back(seq[0].second);
+              words.push_back(seq.size() > 1 ? seq[1].second : (unsigned)(NC + 2));
+              for (size_t i = 0; i < seq.size(); ++i) {
+                if (seq_src[i] >= 0) prog_pos[seq_src[i]] = (int)(words.size() / 2);
+                words.push_back(seq[i].first);
+                words.push_back(i + 2 < seq.size() ? seq[i + 2].second : (unsigned)(NC + 2));
+              }
+            } else {
+              words.push_back((unsigned)(NC + 2));  // header of an empty segment: straight to the end handler
+              words.push_back((unsigned)(NC + 2));
+              words.push_back(0u);
+              words.push_back((unsigned)(NC + 2));
             }
-            words.push_back(0u);
-            words.push_back((unsigned)(NC + 1));  // end of segment
           }
-          for (int i = 0; i < 2; ++i) {  // prefetch slack: the interpreter reads two records past the end
+          for (int i = 0; i < 2; ++i) {  // prefetch slack: the interpreter reads one record past the end
             words.push_back(0u);
-            words.push_back((unsigned)(NC + 1));
+            words.push_back((unsigned)(NC + 2));
           }
           while (words.size() % 4) words.push_back(0u);
           const int len16 = (int)((words.size() - region_start) / 4);
@@ -356,12 +414,15 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   pr.C = g.channels; pr.H = g.height; pr.W = g.width; pr.M = g.num_output; pr.Ho = Ho; pr.Wo = Wo;
   pr.pad_h = g.pad_h; pr.pad_w = g.pad_w; pr.Cg = Cg; pr.Mg = Mg; pr.ngroups = g.group;
   pr.G = G; pr.GP = GP; pr.BR = BR; pr.PX = PX; pr.PY = PY; pr.nbands = nbands; pr.WP = WP; pr.WO = WO;
-  pr.R = R; pr.P = P; pr.plane_f = plane_f; pr.CI = CI; pr.nchunks = nchunks; pr.nblk = nblk; pr.ogroups = ogroups;
+  pr.R = R; pr.P = P; pr.plane_f = plane_f; pr.slot_f = slot_f; pr.use_tma = use_tma ? 1 : 0; pr.HL = HL; pr.CI = CI; pr.nchunks = nchunks; pr.nblk = nblk; pr.ogroups = ogroups;
   pr.nslots = nslots; pr.NS = NS; pr.stage0_off = kBarBytes + tab_bytes; pr.stage_bytes = stage_bytes;
   pr.in_bytes = in_bytes; pr.hdr_bytes = hdr_bytes;
-  pr.n4 = (R * g.width + 6) / 4 + 1;
-  pr.n4_magic = (unsigned)((0x100000000ull + pr.n4 - 1) / pr.n4);
-  pr.ci_magic = (unsigned)((0x100000000ull + CI - 1) / CI);
+  {
+    int lpr = 1, sh = 0;
+    while (lpr < g.width && lpr < 32) { lpr <<= 1; ++sh; }
+    pr.lpr_shift = sh;
+    pr.RO = 32 / lpr;
+  }
   tp->smem_bytes = (size_t)pr.stage0_off + (size_t)NS * stage_bytes;
   tp->nrecords = prog.size() * 2;
 
@@ -371,19 +432,14 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     const std::vector<Slot> slots = enumerate_slots(GP, BR, PX, best.order);
     for (int i = 0; i < nslots; ++i) {
       const Slot &sl = slots[i];
-      lanes[i] = make_int4((sl.gs * plane_f + (sl.pyb * TY * S * P + sl.px * TX * S) * PAIR) * 4, sl.gs, sl.pyb, sl.px);
+      lanes[i] = make_int4((sl.gs * slot_f + (sl.pyb * TY * S * P + lane_col0 + sl.px * TX * S) * PAIR) * 4, sl.gs, sl.pyb,
+                           sl.px);
     }
   }
-  // ---- loader scatter table: element e (row-major over the band's W-wide input rows) -> position offset ----
-  std::vector<unsigned short> dst_off((size_t)R * g.width);
-  for (int r = 0; r < R; ++r)
-    for (int x = 0; x < g.width; ++x) dst_off[(size_t)r * g.width + x] = (unsigned short)(r * P + x + g.pad_w);
-  if ((long)R * P > 65535) { delete tp; return 0; }
-
   int rc = 0;
   if ((rc = upload_vec(&tp->d_lanes, lanes, stream)) || (rc = upload_vec(&tp->d_oc_list, oc_list, stream)) ||
       (rc = upload_vec(&tp->d_prog, prog, stream)) || (rc = upload_vec(&tp->d_rtab, rtab, stream)) ||
-      (rc = upload_vec(&tp->d_dst_off, dst_off, stream)) || (rc = upload_vec(&tp->d_prog_pos, prog_pos, stream))) {
+      (rc = upload_vec(&tp->d_prog_pos, prog_pos, stream))) {
     tile_plan_free(tp);
     return rc;
   }
@@ -392,7 +448,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     tile_plan_free(tp);
     return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
   }
-  pr.lanes = tp->d_lanes; pr.oc_list = tp->d_oc_list; pr.prog = tp->d_prog; pr.rtab = tp->d_rtab; pr.dst_off = tp->d_dst_off;
+  pr.lanes = tp->d_lanes; pr.oc_list = tp->d_oc_list; pr.prog = tp->d_prog; pr.rtab = tp->d_rtab;
   // the attribute belongs to the kernel, not the plan: several plans share a variant, so always raise it to the
   // device's opt-in maximum instead of this plan's own size
   e = cudaFuncSetAttribute(V.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -412,8 +468,31 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
   int nunits = (int)((size_t)prm.n_igroups * prm.nbands * prm.ngroups * prm.ogroups);
   const unsigned grid = (unsigned)std::min(nunits, tp->num_sms);
   const VariantDesc &V = kVariants[tp->vidx];
-  void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&bias, (void *)&fuse_relu, (void *)&top, (void *)&nunits};
-  ESCORT_CUDA(cudaLaunchKernel(V.kernel, dim3(grid), dim3((V.NCW + V.NLW) * 32), args, tp->smem_bytes, stream));
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (prm.use_tma) {
+    // bottom as a 4-D tensor {W, H, C, N}; one box = the band's R rows x P columns of CI channels of one image,
+    // starting at x = -pad_w (out-of-bounds elements read as zero: the halo costs nothing)
+    if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) {
+      set_last_error("escort_sconv_forward: bottom must be 16-byte aligned for the TMA-staged kernel");
+      return ESCORT_EINVAL;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)prm.W, (cuuint64_t)prm.H, (cuuint64_t)prm.C, (cuuint64_t)num};
+    const cuuint64_t strides[3] = {(cuuint64_t)prm.W * 4, (cuuint64_t)prm.H * prm.W * 4,
+                                   (cuuint64_t)prm.C * prm.H * prm.W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)prm.P, (cuuint32_t)prm.R, (cuuint32_t)prm.CI, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(bottom), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("escort_sconv_forward: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+      return ESCORT_EINVAL;
+    }
+  }
+  void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&bias, (void *)&fuse_relu, (void *)&top,
+                  (void *)&nunits, (void *)&tmap};
+  ESCORT_CUDA(cudaLaunchKernel(V.kernel, dim3(grid), dim3(V.NTW * 32), args, tp->smem_bytes, stream));
   return 0;
 }
 
@@ -433,6 +512,64 @@ int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t str
   return 0;
 }
 
+// Interpreter-only microbenchmark (tools/interp_bench.py): synthetic byte-code with `per_load` FMA records per LOAD
+// record, handlers drawn uniformly; reports FMA-pipe utilisation of the dispatch loop alone.
+extern "C" ESCORT_API int escort_interp_bench(int variant, int per_load, int active_warps, int iters, double *ms_host,
+                                              double *tflops_host, int *nc_host) {
+  if (variant < 1 || variant > kNumVariants || !ms_host) return ESCORT_EINVAL;
+  const VariantDesc &V = kVariants[variant - 1];
+  const int NC = V.OT * V.KH * V.KW;
+  const int nfma = 1536;
+  std::vector<uint2> prog;
+  unsigned rng = 12345u;
+  auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+  std::vector<std::pair<unsigned, unsigned>> seq;
+  for (int i = 0; i < nfma; ++i) {
+    if (per_load > 0 && i % per_load == 0) seq.push_back({(unsigned)((next() % 8) * 1024), (unsigned)NC});
+    seq.push_back({__builtin_bit_cast(unsigned, 1e-3f), next() % NC});
+  }
+  seq.push_back({0u, (unsigned)(NC + 2)});
+  prog.push_back(make_uint2(seq[0].second, seq[1].second));
+  for (size_t i = 0; i < seq.size(); ++i)
+    prog.push_back(make_uint2(seq[i].first, i + 2 < seq.size() ? seq[i + 2].second : (unsigned)(NC + 2)));
+  prog.push_back(make_uint2(0u, (unsigned)(NC + 2)));
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  uint2 *d_prog = nullptr;
+  float *d_out = nullptr;
+  ESCORT_CUDA(cudaMalloc((void **)&d_prog, prog.size() * sizeof(uint2)));
+  ESCORT_CUDA(cudaMalloc((void **)&d_out, (size_t)sms * V.NTW * 32 * sizeof(float)));
+  ESCORT_CUDA(cudaMemcpy(d_prog, prog.data(), prog.size() * sizeof(uint2), cudaMemcpyHostToDevice));
+  const size_t smem = 16384 + prog.size() * 8 + 64;
+  ESCORT_CUDA(cudaFuncSetAttribute(V.bench, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  int nrec = (int)prog.size();
+  if (active_warps <= 0 || active_warps > V.NCW) active_warps = V.NCW;
+  void *args[] = {(void *)&d_prog, (void *)&nrec, (void *)&iters, (void *)&active_warps, (void *)&d_out};
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 3; ++rep) {
+    cudaEventRecord(e0, 0);
+    ESCORT_CUDA(cudaLaunchKernel(V.bench, dim3(sms), dim3(V.NTW * 32), args, smem, 0));
+    cudaEventRecord(e1, 0);
+    ESCORT_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0) best = std::min(best, ms);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_prog);
+  cudaFree(d_out);
+  *ms_host = best;
+  const double flops = 2.0 * nfma * (double)V.TY * V.TX * V.PAIR * 32.0 * active_warps * sms * (double)iters;
+  if (tflops_host) *tflops_host = flops / (best * 1e-3) / 1e12;
+  if (nc_host) *nc_host = NC;
+  return 0;
+}
+
 // introspection for tests/bench: tiling summary as a string
 extern "C" ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen) {
   if (!plan || !buf || buflen <= 0) return ESCORT_EINVAL;
@@ -443,9 +580,9 @@ extern "C" ESCORT_API int escort_plan_describe(const escort_plan *plan, char *bu
   const TilePlan *tp = plan->tile;
   const TileParams &p = tp->prm;
   snprintf(buf, buflen,
-           "%s G=%d BR=%d nbands=%d WP=%d WO=%d R=%d P=%d plane_f=%d CI=%d nchunks=%d nblk=%d ogroups=%d nslots=%d NS=%d "
+           "%s%s G=%d BR=%d nbands=%d WP=%d WO=%d R=%d P=%d plane_f=%d CI=%d nchunks=%d nblk=%d ogroups=%d nslots=%d NS=%d "
            "stage=%dB smem=%zu records=%zu",
-           tp->name, p.G, p.BR, p.nbands, p.WP, p.WO, p.R, p.P, p.plane_f, p.CI, p.nchunks, p.nblk, p.ogroups, p.nslots,
+           tp->name, p.use_tma ? " tma" : "", p.G, p.BR, p.nbands, p.WP, p.WO, p.R, p.P, p.plane_f, p.CI, p.nchunks, p.nblk, p.ogroups, p.nslots,
            p.NS, p.stage_bytes, tp->smem_bytes, tp->nrecords);
   return 0;
 }

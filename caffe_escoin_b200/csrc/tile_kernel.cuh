@@ -1,5 +1,7 @@
 // tile_kernel.cuh -- device side of the tile-interpreter forward kernel (design notes in sconv_tile.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace escort {
@@ -18,6 +20,9 @@ struct TileParams {
   int WP, WO;              // pixel warps x channel-block warps (WP*WO == NCW of the variant)
   int R, P;                // staged rows per plane, row pitch in positions
   int plane_f;             // floats per (channel, image slot) plane = R*P*PAIR + skew
+  int slot_f;              // floats per image slot of a stage (>= CI*plane_f); stage = [slot][channel][row][col]
+  int HL;                  // halo columns left of data column 0 in a staged row
+  int use_tma;             // input chunks staged by cp.async.bulk.tensor (W % 4 == 0) instead of per-element cp.async
   int CI, nchunks;         // channels per chunk, chunks per conv group
   int nblk, ogroups;       // channel blocks per conv group, CTAs' channel-block groups per conv group
   int nslots;              // valid lane slots per CTA (<= WP*32)
@@ -28,14 +33,12 @@ struct TileParams {
   int in_bytes;            // CI * GP * plane_f * 4
   int hdr_bytes;           // program-region header (segment offsets), multiple of 16
   int n_igroups;           // filled per launch
-  int n4;                  // loader: 16-byte words per plane window = (R*W + 6)/4 + 1
-  unsigned n4_magic, ci_magic;  // ceil(2^32 / n4), ceil(2^32 / CI) for multiply-high division
   // tables
   const int4 *lanes;       // [WP*32] {lane_base_bytes, image slot, pyb, px}
   const int *oc_list;      // [ngroups*nblk*OT] global out-channel or -1
   const uint4 *prog;       // program regions (16-byte units)
   const int2 *rtab;        // [ngroups*ogroups*nchunks] {offset, length} of a region in 16-byte units
-  const unsigned short *dst_off;  // [R*W] position offset of element e of a plane band (row-major, W wide)
+  int lpr_shift, RO;       // loader: log2(lanes per row), rows per warp-wide copy instruction
 };
 
 #ifndef ESCORT_TILE_DEVICE_ONLY
@@ -49,7 +52,6 @@ struct TilePlan {
   int *d_oc_list;
   uint4 *d_prog;
   int2 *d_rtab;
-  unsigned short *d_dst_off;
   int *d_prog_pos;         // [nnz] row-major nonzero -> index of its record (8-byte units) in d_prog
   size_t nrecords;
   int num_sms;
@@ -102,42 +104,59 @@ __device__ __forceinline__ void cp_async4(unsigned dst_smem, const float *src) {
 __device__ __forceinline__ void cp_async16(unsigned dst_smem, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
+// One warp copies whole plane bands; a warp-wide copy instruction covers RO consecutive rows (lanes = RO rows x LPR
+// columns, LPR = the power of two >= W, capped at 32) or, for W > 32, one 32-column segment of a row.  Per
+// instruction the loop needs a row-bound predicate and two pointer increments -- no table, no division.
 template <int PAIR>
 __device__ __forceinline__ void load_chunk(const TileParams &p, const float *__restrict__ bottom, float *in_s,
-                                           unsigned in_s_addr, const unsigned short *dst_off_s, int n0, int num,
-                                           int cbase, int cend, int ylo, int nrows, int rowshift, bool zero_rows, int lw,
-                                           int nlw, int lane) {
-  const int L = nrows * p.W;
+                                           unsigned in_s_addr, int n0, int num, int cbase, int cend, int ylo, int nrows,
+                                           int rowshift, int lw, int nlw, int lane) {
   const int nplanes = p.CI * p.G;
   const size_t plane_stride = (size_t)p.H * p.W;  // floats between channels
+  const int rsub = lane >> p.lpr_shift, xl = lane & ((1 << p.lpr_shift) - 1);
+  const bool edge = rowshift > 0 || rowshift + nrows < p.R;
+  int g = 0, ci = lw;
+  while (ci >= p.CI) { ci -= p.CI; ++g; }
   for (int pl = lw; pl < nplanes; pl += nlw) {
-    const int g = pl / p.CI, ci = pl - g * p.CI;
     const int c = cbase + ci, n = n0 + g;
-    const int plane_off = (ci * p.GP + g / PAIR) * p.plane_f + (g % PAIR);  // floats
-    if (zero_rows) {
-      // rows outside the image differ between bands: rewrite them as zeros (only when the layer is banded)
+    const int plane_off = (g / PAIR) * p.slot_f + ci * p.plane_f + (g % PAIR);  // floats
+    if (edge) {
+      // rows outside the image differ between bands: rewrite them as zeros (edge bands of a banded layer only)
       float *plane = in_s + plane_off;
       const int lo_end = rowshift * p.P, hi_beg = (rowshift + nrows) * p.P, tot = p.R * p.P;
       for (int i = lane; i < lo_end; i += 32) plane[i * PAIR] = 0.f;
       for (int i = hi_beg + lane; i < tot; i += 32) plane[i * PAIR] = 0.f;
     }
-    if (c >= cend || n >= num) continue;
-    const float *src = bottom + ((size_t)n * p.C + c) * plane_stride + (size_t)ylo * p.W;
-    const unsigned dst = in_s_addr + 4u * (unsigned)(plane_off + rowshift * p.P * PAIR);
+    if (c < cend && n < num) {
+      const float *src0 = bottom + ((size_t)n * p.C + c) * plane_stride + (size_t)ylo * p.W;
+      const unsigned dst0 = in_s_addr + 4u * (unsigned)(plane_off + (rowshift * p.P + p.HL) * PAIR);
+      for (int x = xl; x < p.W; x += 32) {  // one trip unless W > 32
+        const float *src = src0 + rsub * p.W + x;
+        unsigned dst = dst0 + 4u * PAIR * (unsigned)(rsub * p.P + x);
+        const int sstep = p.RO * p.W;
+        const unsigned dstep = 4u * PAIR * (unsigned)(p.RO * p.P);
 #pragma unroll 4
-    for (int e = lane; e < L; e += 32) cp_async4(dst + (unsigned)dst_off_s[e] * (4u * PAIR), src + e);
+        for (int r = rsub; r < nrows; r += p.RO) {
+          cp_async4(dst, src);
+          src += sstep;
+          dst += dstep;
+        }
+      }
+    }
+    ci += nlw;
+    while (ci >= p.CI) { ci -= p.CI; ++g; }
   }
 }
 
-template <int OT, int TY, int TX, int KH, int KW, int S, int PAIR>
-__global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + Interp<OT, TY, TX, KH, KW, S, PAIR>::NLW) * 32, 1)
+template <int VID>
+__global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
     sconv_tile_kernel(const TileParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias,
-                      int fuse_relu, float *__restrict__ top, int nunits) {
-  using IP = Interp<OT, TY, TX, KH, KW, S, PAIR>;
-  constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = (NCW + NLW) * 32;
+                      int fuse_relu, float *__restrict__ top, int nunits, const __grid_constant__ CUtensorMap tmap) {
+  using IP = Interp<VID>;
+  constexpr int OT = IP::OT, TY = IP::TY, TX = IP::TX, S = IP::S, PAIR = IP::PAIR;
+  constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = IP::NTW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
-  unsigned short *dst_off_s = reinterpret_cast<unsigned short *>(smem_raw + kBarBytes);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
 
@@ -154,13 +173,17 @@ __global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + In
     const int n4 = (p.NS * p.stage_bytes) >> 4;
     const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < n4; i += NT) st4[i] = z;
-    const int ntab = p.R * p.W;
-    for (int i = tid; i < ntab; i += NT) dst_off_s[i] = p.dst_off[i];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the TMA path overwrites these bytes
   }
   __syncthreads();
 
   if (wid >= NCW) {
     // ================= loader warps: stream input chunks + byte-code regions through the stage ring ==========
+    if constexpr (IP::CREGS > 0) {
+      // the loader warpgroup hands its registers to the compute warpgroups; its idle warps leave
+      asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+      if (wid >= NCW + NLW) return;
+    }
     const int lw = wid - NCW;
     int it = 0;
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
@@ -175,8 +198,27 @@ __global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + In
         if (k > 0) mbar_wait(empty_bar + 8 * s, (unsigned)((k - 1) & 1));
         unsigned char *stage = smem_raw + p.stage0_off + (size_t)s * p.stage_bytes;
         const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
-        load_chunk<PAIR>(p, bottom, reinterpret_cast<float *>(stage), stage_addr, dst_off_s, uc.n0, num,
-                         cbase0 + c * p.CI, cend, ylo, nrows, rowshift, p.nbands > 1, lw, NLW, lane);
+        if (p.use_tma) {
+          // one bulk-tensor copy per image of the group: box {P, R, CI, 1} at {-HL, y_in0, channel, image} (HL = 4: the
+          // innermost start must be 16-byte aligned); rows /
+          // columns / images outside the tensor arrive as zeros, bytes are counted on the stage's full barrier
+          if (lw == 0 && lane == 0) {
+            const unsigned slot_bytes = (unsigned)(p.P * p.R * p.CI) * 4u;
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(full_bar + 8 * s),
+                         "r"(slot_bytes * (unsigned)p.GP)
+                         : "memory");
+            for (int gi = 0; gi < p.GP; ++gi) {
+              asm volatile(
+                  "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, "
+                  "%4, %5}], [%6];" ::"r"(stage_addr + (unsigned)(gi * p.slot_f) * 4u),
+                  "l"(&tmap), "r"(-p.HL), "r"(y_in0), "r"(cbase0 + c * p.CI), "r"(uc.n0 + gi), "r"(full_bar + 8 * s)
+                  : "memory");
+            }
+          }
+        } else {
+          load_chunk<PAIR>(p, bottom, reinterpret_cast<float *>(stage), stage_addr, uc.n0, num, cbase0 + c * p.CI, cend,
+                           ylo, nrows, rowshift, lw, NLW, lane);
+        }
         {  // byte-code region of this (channel-block group, chunk): contiguous 16-byte async copies
           const int2 r = rt[c];
           const uint4 *src = p.prog + r.x;
@@ -193,6 +235,7 @@ __global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + In
   // ================= compute warps ============================================================================
   // (kept deliberately lean: everything that is live across the interpreter block costs a register on top of the
   // accumulators, so unit coordinates and the lane record are recomputed in the epilogue instead of kept)
+  if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
   const unsigned lane_base_off = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
   const unsigned pitch_bytes = (unsigned)p.P * 4u * PAIR;
   float acc[IP::NACC];
@@ -257,6 +300,37 @@ __global__ void __launch_bounds__((Interp<OT, TY, TX, KH, KW, S, PAIR>::NCW + In
       }
     }
   }
+}
+
+// ---- interpreter-only microbenchmark: no loader, no barriers.  Every active warp walks the same synthetic
+// byte-code (already in the interpreter's record format) `iters` times against a zeroed input area; measures the
+// dispatch + FMA ceiling of a variant in isolation (tools/interp_bench.py).
+template <int VID>
+__global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
+    interp_bench_kernel(const uint2 *__restrict__ prog, int nrec, int iters, int active_warps, float *__restrict__ out) {
+  using IP = Interp<VID>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const int tid = threadIdx.x, wid = tid >> 5;
+  constexpr int kIn = 16384;  // zeroed input area in front of the program
+  for (int i = tid; i < kIn / 4; i += blockDim.x) reinterpret_cast<float *>(smem_raw)[i] = 0.f;
+  for (int i = tid; i < nrec; i += blockDim.x) reinterpret_cast<uint2 *>(smem_raw + kIn)[i] = prog[i];
+  __syncthreads();
+  if (wid >= IP::NCW) {
+    if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
+    return;
+  }
+  if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
+  if (wid >= active_warps) return;
+  float acc[IP::NACC];
+#pragma unroll
+  for (int i = 0; i < IP::NACC; ++i) acc[i] = 0.f;
+#pragma unroll 1
+  for (int it = 0; it < iters; ++it) IP::run(acc, smem_base + kIn, smem_base + (tid & 31) * 16u, 128u * IP::PAIR);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < IP::NACC; ++i) sum += acc[i];
+  out[blockIdx.x * blockDim.x + tid] = sum;
 }
 #endif  // !ESCORT_TILE_HOST_ONLY
 

@@ -10,7 +10,10 @@
 
 namespace escort {
 const void *ESCORT_CAT(tile_variant_kernel_, ESCORT_VARIANT_ID)() {
-  return (const void *)&sconv_tile_kernel<ESCORT_VARIANT_ARGS>;
+  return (const void *)&sconv_tile_kernel<ESCORT_VARIANT_ID>;
 }
-const char *ESCORT_CAT(tile_variant_name_, ESCORT_VARIANT_ID)() { return Interp<ESCORT_VARIANT_ARGS>::name(); }
+const void *ESCORT_CAT(tile_variant_bench_, ESCORT_VARIANT_ID)() {
+  return (const void *)&interp_bench_kernel<ESCORT_VARIANT_ID>;
+}
+const char *ESCORT_CAT(tile_variant_name_, ESCORT_VARIANT_ID)() { return Interp<ESCORT_VARIANT_ID>::name(); }
 }  // namespace escort

@@ -105,6 +105,8 @@ ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int bufl
 /* tuning knob for tests/bench: force a forward variant (-1 auto, 0 generic, >0 tile-interpreter variants) */
 ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
 
+/* tuning knob: variant as above plus which of the planner's tiling candidates to use (0 = its favourite) */
+ESCORT_API int escort_plan_set_config(escort_plan *plan, int variant, int layout_rank);
 /* measure every forward variant that supports the geometry on a scratch batch of `num` images and keep the
  * fastest (plan-time selection, like cuDNN's find); synchronises `stream`.  Optional: without it the plan
  * uses a static default. */

@@ -45,26 +45,54 @@ VARIANTS = [
     # 3x3 stride 2
     (8, 2, 4, 3, 3, 2, 1, 14, 2),
     (4, 2, 4, 3, 3, 2, 2, 6, 2),
+    # ---- second generation: more FMAs per dispatched record at >= 2 warps per scheduler.  The register file is
+    # split per scheduler (16K registers each): 8 / 12 / 16 warps per CTA allow 255 / 168 / 128 registers; a trailing
+    # CREGS re-balances registers between the loader warpgroup and the compute warpgroups (setmaxnreg) ----
+    (6, 4, 4, 3, 3, 1, 1, 10, 2),        # 16
+    (7, 4, 4, 3, 3, 1, 1, 10, 2),
+    (3, 7, 4, 3, 3, 1, 1, 10, 2),
+    (6, 7, 4, 3, 3, 1, 1, 6, 2),
+    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232),    # 20
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232),
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152),
+    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232),
+    (4, 4, 4, 5, 5, 1, 1, 10, 2),
+    (5, 4, 4, 5, 5, 1, 1, 10, 2),        # 25
+    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232),
+    (6, 4, 4, 5, 5, 1, 1, 8, 4, 232),
 ]
 
 
-def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
+def gen_variant(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0):
     NACC = OT * TY * TX               # accumulator registers (32-bit for PAIR 1, 64-bit pairs for PAIR 2)
     PR = (TY - 1) * S + KH            # patch rows held in registers
     PC = (TX - 1) * S + KW            # patch cols needed
     per_vec = 4 // PAIR               # positions per 128-bit shared load
-    half = per_vec // 2               # positions per 64-bit shared load (0 for PAIR 2: one position = 64 bits)
-    # per-row load plan: 128-bit loads, with a 64-bit tail when that saves registers
-    loads = []                        # (position offset, positions)
+    # per-row load plans (register offset in the row, positions, byte offset from the lane base).
+    # plan B ("patch aligned", handler NC): the lane base is the patch's first column, 16-byte aligned; 128-bit
+    #   loads with a 64-bit tail.  Used when rows are staged element-wise (the halo is pad_w columns wide).
+    # plan A ("aligned body", handler NC+1, PAIR 1 only): the lane base is the tile's first OUTPUT column; data
+    #   column 0 sits on a 16-byte boundary -- what TMA staging produces -- and the PADL halo columns to its left and
+    #   the tail are fetched with naturally aligned narrower loads.
+    PADL = (KW - 1) // 2
+    loads = []
     pos = 0
     while pos < PC:
         rem = PC - pos
         if PAIR == 1 and rem <= 2:
-            loads.append((pos, 2)); pos += 2
+            loads.append((pos, 2, pos * 4)); pos += 2
         elif PAIR == 2 and rem == 1:
-            loads.append((pos, 1)); pos += 1
+            loads.append((pos, 1, pos * 8)); pos += 1
         else:
-            loads.append((pos, per_vec)); pos += per_vec
+            loads.append((pos, per_vec, pos * 4 * PAIR)); pos += per_vec
+    loads_a = []
+    if PAIR == 1:
+        c = -PADL
+        while c < PC - PADL:
+            rem = PC - PADL - c
+            n = 4 if (c % 4 == 0 and rem >= 4) else 2 if (c % 2 == 0 and rem >= 2) else 1
+            loads_a.append((c + PADL, n, c * 4))
+            c += n
     XW = pos                          # positions per patch row actually loaded
     NX = PR * XW
     NC = OT * KH * KW
@@ -78,25 +106,25 @@ def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
         a(".reg .b64 x<%d>, ww, a<%d>;" % (NX, NACC))
         for i in range(NACC):
             a("mov.b64 a%d, {%%%d, %%%d};" % (i, 2 * i, 2 * i + 1))
-    a(".reg .b32 wcur, wnxt, cnxt, wnn, cnn, ctmp, pc, ad<%d>;" % PR)
-    # Threaded code.  Register protocol at a handler's entry: wcur = payload of the record being executed,
-    # (wnxt, cnxt) = the following record (cnxt = which handler runs next), pc -> the record after that.
-    # Each handler first fetches record i+2 into (wnn, cnn) so the shared-memory latency and the jump-table lookup
-    # for cnxt both overlap its FMAs, then rotates the registers and branches with its own brx.idx.
+    a(".reg .b32 wcur, c1, c2, cj, pc, ad<%d>;" % PR)
+    # Threaded code.  Record i = {payload_i, handler_{i+2}}: a record carries its own payload and the id of the
+    # handler that runs two records later.  Register protocol at a handler's entry: wcur = payload of the record
+    # being executed (its shared-memory load may still be in flight: it was issued just before the branch and
+    # overlaps the branch's own bubble), c1 = id of the next handler (ready, so the jump-table lookup that brx.idx
+    # expands to starts at the top of the handler and hides behind the FMAs), c2 = id of the handler after that
+    # (in flight), pc -> the next record.  No payload register rotation; one move per record.
     a("mov.u32 pc, %%%d;" % NOPS)
-    a("ld.shared.v2.b32 {wcur, ctmp}, [pc];")
-    a("ld.shared.v2.b32 {wnxt, cnxt}, [pc+8];")
+    a("ld.shared.v2.b32 {cj, c1}, [pc];")         # header: {handler_0, handler_1}
+    a("ld.shared.v2.b32 {wcur, c2}, [pc+8];")     # record 0: {payload_0, handler_2}
     a("add.u32 pc, pc, 16;")
-    targets = ["HF%d" % c for c in range(NC)] + ["HLOAD", "HEND"]
+    targets = ["HF%d" % c for c in range(NC)] + ["HLOAD", "HLOADA" if PAIR == 1 else "HLOAD", "HEND"]
     a("TL: .branchtargets %s;" % ", ".join(targets))
-    a("brx.idx ctmp, TL;")
-    fetch = "ld.shared.v2.b32 {wnn, cnn}, [pc];"
-    adv = ["mov.b32 wcur, wnxt;", "mov.b32 wnxt, wnn;", "mov.b32 ctmp, cnxt;", "mov.b32 cnxt, cnn;",
-           "add.u32 pc, pc, 8;", "brx.idx ctmp, TL;"]
+    a("brx.idx.uni cj, TL;")
+    adv = ["mov.b32 c1, c2;", "ld.shared.v2.b32 {wcur, c2}, [pc];", "add.u32 pc, pc, 8;", "brx.idx.uni cj, TL;"]
     for c in range(NC):
         o, kh, kw = c // (KH * KW), (c // KW) % KH, c % KW
         a("HF%d:" % c)
-        a(fetch)
+        a("mov.b32 cj, c1;")
         if PAIR == 2:
             a("mov.b64 ww, {wcur, wcur};")
         for ty in range(TY):
@@ -108,26 +136,31 @@ def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
                 else:
                     a("fma.rn.f32x2 a%d, ww, x%d, a%d;" % (acc, xi, acc))
         L.extend(adv)
-    a("HLOAD:")
-    a(fetch)
-    # wcur = byte offset of the input-channel plane inside the staged chunk; %NACC+1 = lane base address (shared,
-    # bytes); %NACC+2 = row pitch in bytes
-    a("add.u32 ad0, %%%d, wcur;" % (NOPS + 1))
-    for r in range(1, PR):
-        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
-    for r in range(PR):
-        for (po, cnt) in loads:
-            b = r * XW + po
-            byte = po * 4 * PAIR
-            if PAIR == 1 and cnt == 4:
-                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d+%d];" % (b, b + 1, b + 2, b + 3, r, byte))
-            elif PAIR == 1:
-                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d+%d];" % (b, b + 1, r, byte))
-            elif cnt == 2:
-                a("ld.shared.v2.b64 {x%d, x%d}, [ad%d+%d];" % (b, b + 1, r, byte))
-            else:
-                a("ld.shared.b64 x%d, [ad%d+%d];" % (b, r, byte))
-    L.extend(adv)
+    for label, plan in (("HLOAD", loads), ("HLOADA", loads_a)):
+        if not plan:
+            continue
+        a(label + ":")
+        a("mov.b32 cj, c1;")
+        # wcur = byte offset of the input-channel plane inside the staged chunk; %NOPS+1 = lane base address (shared,
+        # bytes); %NOPS+2 = row pitch in bytes
+        a("add.u32 ad0, %%%d, wcur;" % (NOPS + 1))
+        for r in range(1, PR):
+            a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
+        for r in range(PR):
+            for (po, cnt, byte) in plan:
+                b = r * XW + po
+                sgn = "+%d" % byte
+                if PAIR == 1 and cnt == 4:
+                    a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+                elif PAIR == 1 and cnt == 2:
+                    a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+                elif PAIR == 1:
+                    a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+                elif cnt == 2:
+                    a("ld.shared.v2.b64 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+                else:
+                    a("ld.shared.b64 x%d, [ad%d%s];" % (b, r, sgn))
+        L.extend(adv)
     a("HEND:")
     if PAIR == 2:
         for i in range(NACC):
@@ -135,14 +168,19 @@ def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
     a("}")
     body = "\n".join('      "%s\\n\\t"' % s for s in L)
     ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
-    name = "o%d_y%d_x%d_k%dx%d_s%d_p%d_w%d" % (OT, TY, TX, KH, KW, S, PAIR, NCW)
+    name = "o%d_y%d_x%d_k%dx%d_s%d_p%d_w%d%s" % (OT, TY, TX, KH, KW, S, PAIR, NCW, "_r%d" % CREGS if CREGS else "")
     src = []
     src.append("// ---- variant %s: %d accumulator registers%s, %d patch registers, %d handlers ----"
                % (name, NACC, "" if PAIR == 1 else " (64-bit pairs)", NX, NC + 2))
-    src.append("template <> struct Interp<%d, %d, %d, %d, %d, %d, %d> {" % (OT, TY, TX, KH, KW, S, PAIR))
-    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d;  // NACC fp32 accumulators"
-               % (NOPS, NC, PR, PC, XW))
-    src.append("  static constexpr int NCW = %d, NLW = %d;" % (NCW, NLW))
+    src.append("template <> struct Interp<%d> {" % vid)
+    src.append("  static constexpr int OT = %d, TY = %d, TX = %d, KH = %d, KW = %d, S = %d, PAIR = %d;"
+               % (OT, TY, TX, KH, KW, S, PAIR))
+    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;  // NACC fp32 accumulators"
+               % (NOPS, NC, PR, PC, XW, PADL))
+    # CREGS > 0: the loader warps form a warpgroup of their own (4 warps, NLW of them active) that gives its
+    # registers back with setmaxnreg.dec and the compute warpgroups grow to CREGS with setmaxnreg.inc
+    NTW = NCW + (4 if CREGS else NLW)
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d;" % (NCW, NLW, NTW, CREGS))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base,"
                % NOPS)
@@ -160,18 +198,23 @@ def gen_variant(OT, TY, TX, KH, KW, S, PAIR, NCW, NLW):
 def main():
     os.makedirs(OUTDIR, exist_ok=True)
     head = ["// GENERATED by tools/gen_interp.py -- do not edit.  Inline-PTX threaded-code interpreter for one tile shape.",
-            "// Record stream (shared memory): 8-byte records {u32 payload, u32 handler}; handler < NC: FMA (payload =",
-            "// fp32 weight), handler == NC: LOAD patch (payload = byte offset of the channel plane), NC+1: end of segment.",
+            "// Record stream (shared memory): a header {handler_0, handler_1} then 8-byte records {u32 payload_i, u32 handler_(i+2)};",
+            "// handler < NC: FMA (payload = fp32 weight), handler == NC / NC+1: LOAD patch, patch-aligned / aligned-body plan (payload = byte",
+            "// offset of the channel plane), NC+2: end of segment.",
             "#pragma once",
-            "template <int OT, int TY, int TX, int KH, int KW, int S, int PAIR> struct Interp;"]
+            "template <int VID> struct Interp;"]
     for i, v in enumerate(VARIANTS):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
-        txt = "\n".join(head + [gen_variant(*v), "#define ESCORT_VARIANT_ARGS %d, %d, %d, %d, %d, %d, %d" % v[:7]]) + "\n"
+        txt = "\n".join(head + [gen_variant(i, *v)]) + "\n"
         if not os.path.exists(path) or open(path).read() != txt:
             open(path, "w").write(txt)
     lst = os.path.join(OUTDIR, "variant_list.inc")
     txt = "// GENERATED by tools/gen_interp.py\n#define ESCORT_NUM_VARIANTS %d\n#define ESCORT_VARIANT_LIST(X) \\\n" % len(VARIANTS)
-    txt += " \\\n".join("  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + v) for i, v in enumerate(VARIANTS)) + "\n"
+    def row(i, v):
+        cregs = v[9] if len(v) > 9 else 0
+        ntw = v[7] + (4 if cregs else v[8])
+        return "  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + tuple(v[:9]) + (ntw,))
+    txt += " \\\n".join(row(i, v) for i, v in enumerate(VARIANTS)) + "\n"
     if not os.path.exists(lst) or open(lst).read() != txt:
         open(lst, "w").write(txt)
     print("generated %d variants in %s" % (len(VARIANTS), OUTDIR))

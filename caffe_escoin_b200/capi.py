@@ -23,7 +23,7 @@ class Geom(C.Structure):
 
 EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
            "escort_plan_destroy", "escort_plan_nnz", "escort_plan_kernel_name", "escort_plan_describe",
-           "escort_plan_set_variant", "escort_plan_set_config", "escort_plan_autotune",
+           "escort_plan_set_variant", "escort_plan_set_config", "escort_plan_get_config", "escort_plan_autotune",
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_measure_fp32_peak",
            "escort_last_error", "escort_version"]
@@ -37,6 +37,7 @@ lib.escort_plan_nnz.argtypes = [C.c_void_p]
 lib.escort_plan_destroy.argtypes = [C.c_void_p]
 lib.escort_plan_set_variant.argtypes = [C.c_void_p, C.c_int]
 lib.escort_plan_set_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
+lib.escort_plan_get_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.escort_plan_autotune.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 
@@ -153,6 +154,11 @@ class Plan:
 
     def set_config(self, v, rank):
         _check(lib.escort_plan_set_config(self.h, int(v), int(rank)), "escort_plan_set_config")
+
+    def get_config(self):
+        v, r = C.c_int(0), C.c_int(0)
+        _check(lib.escort_plan_get_config(self.h, C.byref(v), C.byref(r)), "escort_plan_get_config")
+        return v.value, r.value
 
     def autotune(self, num, stream=None):
         _check(lib.escort_plan_autotune(self.h, int(num), _stream(stream)), "escort_plan_autotune")

@@ -452,6 +452,13 @@ extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
   return escort_plan_set_config(p, variant, 0);
 }
 
+extern "C" int escort_plan_get_config(const escort_plan *p, int *variant_host, int *layout_rank_host) {
+  ESCORT_REQUIRE(p, "escort_plan_get_config: null plan");
+  if (variant_host) *variant_host = p->variant;
+  if (layout_rank_host) *layout_rank_host = p->layout_rank;
+  return 0;
+}
+
 extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_rank) {
   ESCORT_REQUIRE(p && layout_rank >= 0, "escort_plan_set_config: bad arguments");
   p->layout_rank = layout_rank;

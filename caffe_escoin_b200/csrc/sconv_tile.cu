@@ -111,16 +111,33 @@ bool tile_variant_applies(const escort_plan *plan, int variant) {
          g.dilation_h == 1 && g.dilation_w == 1;
 }
 
-// Pick the default variant for a geometry (auto mode); returns -1 if the tile kernel does not apply.
+// Pick the default variant for a geometry (auto mode, no autotune); returns -1 if the tile kernel does not apply.
+// The preference lists come from the B200 sweeps in profiles/ (escort_plan_autotune measures instead of guessing).
 static int choose_variant(const escort_geom &g, double density) {
-  int best = -1;
+  struct Pref { int KH, S, OT, TY, TX, PAIR, NCW; };
+  static const Pref prefs[] = {
+      {3, 1, 2, 7, 4, 1, 12}, {3, 1, 4, 7, 4, 1, 8}, {3, 1, 2, 4, 4, 1, 16},
+      {5, 1, 4, 4, 4, 1, 10}, {5, 1, 4, 2, 4, 2, 6},
+      {1, 1, 8, 2, 4, 1, 16}, {3, 2, 8, 2, 4, 1, 14},
+  };
+  const bool low_density = density < 0.18;  // few records per patch load: image-paired FFMA2 amortises best
+  if (low_density && g.kernel_h == 3 && g.stride_h == 1)
+    for (int i = 0; i < kNumVariants; ++i) {
+      const VariantDesc &v = kVariants[i];
+      if (v.KH == 3 && v.KW == 3 && v.S == 1 && v.OT == 4 && v.TY == 4 && v.TX == 4 && v.PAIR == 2 && v.NCW == 8) return i;
+    }
+  for (const Pref &p : prefs)
+    for (int i = 0; i < kNumVariants; ++i) {
+      const VariantDesc &v = kVariants[i];
+      if (v.KH != g.kernel_h || v.KW != g.kernel_w || v.S != g.stride_h) continue;
+      if (v.KH == p.KH && v.S == p.S && v.OT == p.OT && v.TY == p.TY && v.TX == p.TX && v.PAIR == p.PAIR && v.NCW == p.NCW)
+        return i;
+    }
   for (int i = 0; i < kNumVariants; ++i) {
     const VariantDesc &v = kVariants[i];
-    if (v.KH != g.kernel_h || v.KW != g.kernel_w || v.S != g.stride_h) continue;
-    if (best < 0) best = i;  // the generator lists the preferred shape of each kernel size first
+    if (v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h) return i;
   }
-  (void)density;
-  return best;
+  return -1;
 }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)

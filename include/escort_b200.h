@@ -107,6 +107,8 @@ ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
 
 /* tuning knob: variant as above plus which of the planner's tiling candidates to use (0 = its favourite) */
 ESCORT_API int escort_plan_set_config(escort_plan *plan, int variant, int layout_rank);
+/* the configuration in force (as chosen by escort_plan_autotune or set explicitly); lets a host cache tuning results */
+ESCORT_API int escort_plan_get_config(const escort_plan *plan, int *variant_host, int *layout_rank_host);
 /* measure every forward variant that supports the geometry on a scratch batch of `num` images and keep the
  * fastest (plan-time selection, like cuDNN's find); synchronises `stream`.  Optional: without it the plan
  * uses a static default. */

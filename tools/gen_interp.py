@@ -60,6 +60,10 @@ VARIANTS = [
     (5, 4, 4, 5, 5, 1, 1, 10, 2),        # 25
     (4, 7, 4, 5, 5, 1, 1, 8, 4, 232),
     (6, 4, 4, 5, 5, 1, 1, 8, 4, 232),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152),   # 28
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152),
+    (2, 7, 4, 3, 3, 1, 1, 14, 2),
+    (2, 7, 4, 5, 5, 1, 1, 12, 4, 152),
 ]
 
 

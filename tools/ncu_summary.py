@@ -35,7 +35,11 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(io.StringIO(src)))
 hdr = rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
-data = rows[2:]
+data = []
+for r in rows[2:]:
+    if len(r) < len(hdr):
+        break  # next kernel's section
+    data.append(r)
 S = lambda r, k: int(r[ix[k]] or 0)
 tot = sum(S(r, "# Samples") for r in data)
 print("total samples", tot, "instructions", len(data))

@@ -113,7 +113,11 @@ def cpu_reference_run(specs, sample, steps, warmup):
     from oracle import pyoracle as po
     po.build()
     kind = "reference" if po.have_ref() else "port"
-    threads = po.ref().ref_max_threads() if po.have_ref() else po.lib().oracle_max_threads()
+    # all host cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not the reference's set-up)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     layers = []
     for li, spec in enumerate(specs):
         n = min(sample, spec.N)

@@ -36,14 +36,14 @@ namespace escort {
 // variant table
 // ------------------------------------------------------------------------------------------------------
 struct VariantDesc {
-  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW;
+  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE;
   const char *name;
   const void *kernel;
   const void *bench;
 };
 
 // one translation unit per variant (tile_variant.cu compiled with -DESCORT_VARIANT_ID=k) exports these
-#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW) \
+#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
   const void *tile_variant_kernel_##ID();                         \
   const void *tile_variant_bench_##ID();                          \
   const char *tile_variant_name_##ID();
@@ -53,8 +53,8 @@ static const VariantDesc *variants() {
   static VariantDesc tab[kNumVariants];
   static bool init = false;
   if (!init) {
-#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW) \
-  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID()};
+#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
+  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID()};
     ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
     init = true;
   }
@@ -215,8 +215,10 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int XW = PAIR == 2 ? PC : (PC % 4 == 0 ? PC : (PC % 4 <= 2 ? PC - PC % 4 + 2 : PC - PC % 4 + 4));
   // TMA staging (cp.async.bulk.tensor with out-of-bounds zero fill = the halo) needs 16-byte global strides and a
   // 16-byte aligned innermost start coordinate, hence the aligned-body row layout
+  // (sieve variants are compiled for one patch-load plan: MODE 1 = aligned body = TMA rows, MODE 2 = patch aligned)
   const bool use_tma = PAIR == 1 && g.width % 4 == 0 && g.pad_w == (KW - 1) / 2 && tma_encoder() != nullptr &&
-                       !getenv("ESCORT_NO_TMA");
+                       !getenv("ESCORT_NO_TMA") && V.MODE != 2 && V.MODE != 4;
+  if ((V.MODE == 1 || V.MODE == 3) && !use_tma) return 0;
   // PAIR 1: data column 0 sits on a 16-byte boundary, HL halo columns to its left (aligned-body layout: TMA and the
   // lanes' 128-bit loads both need it); PAIR 2: the halo is exactly pad_w positions wide.
   const int PADL = use_tma ? (KW - 1) / 2 : 0;
@@ -360,6 +362,108 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
           for (int ow = 0; ow < WO; ++ow) {
             const int blk = og * WO + ow;
             words[region_start + ow] = (unsigned)((words.size() - region_start) * 4);  // byte offset of the segment
+            if (V.MODE >= 3) {
+              // rows stream (16-byte quads): H_0 | H_1 R_0.. | H_2 R_1.. | ... | H_END R_(n-1).. | slack quad; H = {plane
+              // byte offset (END = ~0), mask words, pad}; R = the KW weights of one nonempty kernel row (absent taps 0),
+              // rows of a step in (oc_local, kh) order.  Bit layout as in the sieve stream.
+              const int OPW = std::max(1, 32 / (KH * KW)), NW = ceil_div(OT, OPW);
+              const int HW = NW <= 3 ? 4 : 8, RW = KW <= 4 ? 4 : 8;
+              struct RStep { unsigned off; unsigned m[8]; std::vector<unsigned> w; std::vector<std::pair<int, int>> src; };
+              std::vector<RStep> steps;
+              if (blk < nblk) {
+                std::vector<Rec> &v = buckets[((size_t)gi * nblk + blk) * nchunks + c];
+                std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
+                  if (a.ic != b.ic) return a.ic < b.ic;
+                  if (a.o != b.o) return a.o < b.o;
+                  if (a.kh != b.kh) return a.kh < b.kh;
+                  return a.kw < b.kw;
+                });
+                int cur_ic = -1, cur_row = -1;
+                for (const Rec &r : v) {
+                  if (r.ic != cur_ic) {
+                    cur_ic = r.ic;
+                    cur_row = -1;
+                    steps.emplace_back();
+                    steps.back().off = (unsigned)((r.ic - c * CI) * (long)plane_f * 4);
+                    memset(steps.back().m, 0, sizeof(steps.back().m));
+                  }
+                  RStep &st = steps.back();
+                  if (r.o * KH + r.kh != cur_row) {
+                    cur_row = r.o * KH + r.kh;
+                    st.w.resize(st.w.size() + RW, 0u);
+                  }
+                  st.m[r.o / OPW] |= 1u << (((r.o % OPW) * KH + r.kh) * KW + r.kw);
+                  st.src.push_back({(int)(st.w.size() - RW + r.kw), r.src});
+                  st.w[st.w.size() - RW + r.kw] = __builtin_bit_cast(unsigned, r.val);
+                }
+              }
+              auto emit_rhdr = [&](size_t i) {
+                const size_t at = words.size();
+                words.resize(at + HW, 0u);
+                if (i < steps.size()) {
+                  words[at] = steps[i].off;
+                  for (int k = 0; k < NW; ++k) words[at + 1 + k] = steps[i].m[k];
+                } else {
+                  words[at] = 0xffffffffu;
+                }
+              };
+              emit_rhdr(0);
+              for (size_t i = 0; i < steps.size(); ++i) {
+                emit_rhdr(i + 1);
+                const size_t at = words.size();
+                for (auto &sv : steps[i].src) prog_pos[sv.second] = (int)(at + sv.first);
+                words.insert(words.end(), steps[i].w.begin(), steps[i].w.end());
+              }
+              words.resize(words.size() + 8, 0u);  // the weight prefetch reads up to two quads past the last row
+              continue;
+            }
+            if (V.MODE >= 1) {
+              // sieve stream (4-byte words): H_0 | H_1 W_0.. | H_2 W_1.. | ... | H_END W_(n-1)..  with
+              // H = {byte offset of the channel plane (END = ~0), mask words}; bit of handler (o, kh, kw) =
+              // ((o % OPW) * KH + kh) * KW + kw of word o / OPW; weights of a step in handler order
+              const int OPW = std::max(1, 32 / (KH * KW)), NW = ceil_div(OT, OPW);
+              struct Step { unsigned off; unsigned m[8]; std::vector<std::pair<unsigned, int>> w; };
+              std::vector<Step> steps;
+              if (blk < nblk) {
+                std::vector<Rec> &v = buckets[((size_t)gi * nblk + blk) * nchunks + c];
+                std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
+                  if (a.ic != b.ic) return a.ic < b.ic;
+                  if (a.o != b.o) return a.o < b.o;
+                  if (a.kh != b.kh) return a.kh < b.kh;
+                  return a.kw < b.kw;
+                });
+                int cur_ic = -1;
+                for (const Rec &r : v) {
+                  if (r.ic != cur_ic) {
+                    cur_ic = r.ic;
+                    steps.emplace_back();
+                    steps.back().off = (unsigned)((r.ic - c * CI) * (long)plane_f * 4);
+                    memset(steps.back().m, 0, sizeof(steps.back().m));
+                  }
+                  steps.back().m[r.o / OPW] |= 1u << (((r.o % OPW) * KH + r.kh) * KW + r.kw);
+                  steps.back().w.push_back({__builtin_bit_cast(unsigned, r.val), r.src});
+                }
+              }
+              auto emit_hdr = [&](size_t i) {
+                if (i < steps.size()) {
+                  words.push_back(steps[i].off);
+                  for (int k = 0; k < NW; ++k) words.push_back(steps[i].m[k]);
+                } else {
+                  words.push_back(0xffffffffu);
+                  for (int k = 0; k < NW; ++k) words.push_back(0u);
+                }
+              };
+              emit_hdr(0);
+              for (size_t i = 0; i < steps.size(); ++i) {
+                emit_hdr(i + 1);
+                for (auto &wv : steps[i].w) {
+                  prog_pos[wv.second] = (int)words.size();
+                  words.push_back(wv.first);
+                }
+              }
+              words.push_back(0u);  // the weight prefetch reads one word past the last weight
+              continue;
+            }
             if (blk < nblk) {
               std::vector<Rec> &v = buckets[((size_t)gi * nblk + blk) * nchunks + c];
               std::sort(v.begin(), v.end(), [](const Rec &a, const Rec &b) {
@@ -386,7 +490,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
               words.push_back(seq[0].second);
               words.push_back(seq.size() > 1 ? seq[1].second : (unsigned)(NC + 2));
               for (size_t i = 0; i < seq.size(); ++i) {
-                if (seq_src[i] >= 0) prog_pos[seq_src[i]] = (int)(words.size() / 2);
+                if (seq_src[i] >= 0) prog_pos[seq_src[i]] = (int)words.size();
                 words.push_back(seq[i].first);
                 words.push_back(i + 2 < seq.size() ? seq[i + 2].second : (unsigned)(NC + 2));
               }
@@ -514,17 +618,17 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
 }
 
 __global__ void tile_refresh_kernel(long nnz, const float *__restrict__ w_dense, const int *__restrict__ dense_idx,
-                                    const int *__restrict__ prog_pos, uint2 *__restrict__ prog) {
+                                    const int *__restrict__ prog_pos, unsigned *__restrict__ prog) {
   const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= nnz) return;
-  prog[prog_pos[j]].x = __float_as_uint(__ldg(w_dense + dense_idx[j]));
+  prog[prog_pos[j]] = __float_as_uint(__ldg(w_dense + dense_idx[j]));  // prog_pos = 4-byte word index of the weight
 }
 
 int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream) {
   TilePlan *tp = plan->tile;
   const unsigned blocks = (unsigned)((plan->nnz + 255) / 256);
   tile_refresh_kernel<<<blocks, 256, 0, stream>>>(plan->nnz, weights_dense, plan->d_dense_idx, tp->d_prog_pos,
-                                                  reinterpret_cast<uint2 *>(tp->d_prog));
+                                                  reinterpret_cast<unsigned *>(tp->d_prog));
   ESCORT_LAUNCH_CHECK();
   return 0;
 }
@@ -536,10 +640,68 @@ extern "C" ESCORT_API int escort_interp_bench(int variant, int per_load, int act
   if (variant < 1 || variant > kNumVariants || !ms_host) return ESCORT_EINVAL;
   const VariantDesc &V = kVariants[variant - 1];
   const int NC = V.OT * V.KH * V.KW;
-  const int nfma = 1536;
+  int nfma = 1536;
   std::vector<uint2> prog;
   unsigned rng = 12345u;
   auto next = [&]() { rng = rng * 1664525u + 1013904223u; return rng >> 8; };
+  if (V.MODE >= 3) {
+    // rows variants: `per_load` = density in percent; 64 input-channel steps with random masks
+    const int KK = V.KH * V.KW, OPW = std::max(1, 32 / KK), NW = ceil_div(V.OT, OPW), nsteps = 64;
+    const int HW = NW <= 3 ? 4 : 8, RW = V.KW <= 4 ? 4 : 8;
+    std::vector<unsigned> words;
+    std::vector<std::vector<unsigned>> masks(nsteps, std::vector<unsigned>(NW, 0u));
+    std::vector<int> nrows(nsteps, 0);
+    nfma = 0;
+    for (int i = 0; i < nsteps; ++i) {
+      for (int o = 0; o < V.OT; ++o)
+        for (int kh = 0; kh < V.KH; ++kh) {
+          bool any = false;
+          for (int kw = 0; kw < V.KW; ++kw)
+            if ((int)(next() % 100) < per_load) { masks[i][o / OPW] |= 1u << ((o % OPW) * KK + kh * V.KW + kw); any = true; nfma++; }
+          if (any) nrows[i]++;
+        }
+      if (nrows[i] == 0) { masks[i][0] = 1u; nrows[i] = 1; nfma++; }
+    }
+    auto rhdr = [&](int i) {
+      const size_t at = words.size();
+      words.resize(at + HW, 0u);
+      if (i < nsteps) { words[at] = (next() % 8) * 1024u; for (int k = 0; k < NW; ++k) words[at + 1 + k] = masks[i][k]; }
+      else words[at] = 0xffffffffu;
+    };
+    rhdr(0);
+    for (int i = 0; i < nsteps; ++i) {
+      rhdr(i + 1);
+      for (int k = 0; k < nrows[i] * RW; ++k) words.push_back(k % RW < V.KW ? __builtin_bit_cast(unsigned, 1e-3f) : 0u);
+    }
+    words.resize(words.size() + 8, 0u);
+    for (size_t i = 0; i < words.size(); i += 2) prog.push_back(make_uint2(words[i], words[i + 1]));
+  } else
+  if (V.MODE >= 1) {
+    // sieve variants: `per_load` = density in percent; 64 input-channel steps with random masks
+    const int KK = V.KH * V.KW, OPW = std::max(1, 32 / KK), NW = ceil_div(V.OT, OPW), nsteps = 64;
+    std::vector<unsigned> words;
+    std::vector<std::vector<unsigned>> masks(nsteps, std::vector<unsigned>(NW, 0u));
+    std::vector<int> cnt(nsteps, 0);
+    nfma = 0;
+    for (int i = 0; i < nsteps; ++i) {
+      for (int o = 0; o < V.OT; ++o)
+        for (int k = 0; k < KK; ++k)
+          if ((int)(next() % 100) < per_load) { masks[i][o / OPW] |= 1u << ((o % OPW) * KK + k); cnt[i]++; }
+      if (cnt[i] == 0) { masks[i][0] = 1u; cnt[i] = 1; }
+      nfma += cnt[i];
+    }
+    auto hdr = [&](int i) {
+      if (i < nsteps) { words.push_back((next() % 8) * 1024u); for (int k = 0; k < NW; ++k) words.push_back(masks[i][k]); }
+      else { words.push_back(0xffffffffu); for (int k = 0; k < NW; ++k) words.push_back(0u); }
+    };
+    hdr(0);
+    for (int i = 0; i < nsteps; ++i) {
+      hdr(i + 1);
+      for (int k = 0; k < cnt[i]; ++k) words.push_back(__builtin_bit_cast(unsigned, 1e-3f));
+    }
+    for (int i = 0; i < 4 || words.size() % 2; ++i) words.push_back(0u);
+    for (size_t i = 0; i < words.size(); i += 2) prog.push_back(make_uint2(words[i], words[i + 1]));
+  } else {
   std::vector<std::pair<unsigned, unsigned>> seq;
   for (int i = 0; i < nfma; ++i) {
     if (per_load > 0 && i % per_load == 0) seq.push_back({(unsigned)((next() % 8) * 1024), (unsigned)NC});
@@ -550,6 +712,7 @@ extern "C" ESCORT_API int escort_interp_bench(int variant, int per_load, int act
   for (size_t i = 0; i < seq.size(); ++i)
     prog.push_back(make_uint2(seq[i].first, i + 2 < seq.size() ? seq[i + 2].second : (unsigned)(NC + 2)));
   prog.push_back(make_uint2(0u, (unsigned)(NC + 2)));
+  }
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -52,7 +52,7 @@ struct TilePlan {
   int *d_oc_list;
   uint4 *d_prog;
   int2 *d_rtab;
-  int *d_prog_pos;         // [nnz] row-major nonzero -> index of its record (8-byte units) in d_prog
+  int *d_prog_pos;         // [nnz] row-major nonzero -> 4-byte word index of its weight in d_prog
   size_t nrecords;
   int num_sms;
 };
@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         const unsigned region = stage + p.in_bytes;
         unsigned seg;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(seg) : "r"(region + ow4));
-        IP::run(acc, region + seg, stage + lane_base_off, pitch_bytes);
+        IP::run(acc, region + seg, stage + lane_base_off, pitch_bytes, (unsigned)p.use_tma);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + 8 * s);
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
 #pragma unroll
   for (int i = 0; i < IP::NACC; ++i) acc[i] = 0.f;
 #pragma unroll 1
-  for (int it = 0; it < iters; ++it) IP::run(acc, smem_base + kIn, smem_base + (tid & 31) * 16u, 128u * IP::PAIR);
+  for (int it = 0; it < iters; ++it) IP::run(acc, smem_base + kIn, smem_base + (tid & 31) * 16u, 128u * IP::PAIR, 0u);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < IP::NACC; ++i) sum += acc[i];

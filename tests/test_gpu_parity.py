@@ -93,7 +93,7 @@ def run_forward_all_paths(capi, po, g, w, bias, x, relu, variants=None):
     csr = capi.weight_align(to_dev(w), geom)
     outs = {}
     if variants is None:
-        variants = list(range(-1, 32))
+        variants = list(range(-1, 90))
     for v in variants:
         plan = capi.Plan(geom, csr)
         if v != -1:

@@ -67,6 +67,388 @@ VARIANTS = [
 ]
 
 
+# ---- third generation ("sieve"): no indirect branch at all.  The handlers sit in canonical (oc_local, kh, kw)
+# order and every input channel of a channel block carries a bit mask of the handlers that have a nonzero; the
+# warp falls through the handler chain and skips the absent ones with warp-uniform *direct* forward branches
+# (whole channel / whole kernel row first, then single taps).  Weights are a plain fp32 stream consumed in order.
+# Same tuple layout as VARIANTS.
+SIEVE = [
+    # 3x3 stride 1 (1-based variant ids start at 32).  Trailing letter = patch-load plan the variant is compiled for:
+    # "a" aligned body (rows staged by TMA), "b" patch aligned (rows staged by the cp.async loader)
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),    # 32
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
+    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),
+    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),    # 35
+    (6, 7, 4, 3, 3, 1, 1, 6, 2, 0, "a"),
+    (6, 7, 4, 3, 3, 1, 1, 6, 2, 0, "b"),
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 39
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 42
+    (8, 4, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
+    (10, 4, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
+    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 45
+    (8, 2, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    # 5x5 stride 1
+    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "a"),    # 47
+    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "b"),
+    (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
+    (6, 4, 4, 5, 5, 1, 1, 8, 4, 232, "b"),    # 50
+    # 1x1
+    (8, 2, 4, 1, 1, 1, 1, 16, 4, 104, "b"),
+    (6, 7, 4, 1, 1, 1, 1, 8, 4, 232, "b"),
+    # 3x3 stride 2
+    (4, 4, 4, 3, 3, 2, 1, 8, 4, 232, "b"),    # 53
+    (8, 2, 4, 3, 3, 2, 1, 12, 4, 152, "b"),
+]
+
+
+def load_plans(PC, PAIR, KW):
+    per_vec = 4 // PAIR
+    PADL = (KW - 1) // 2
+    loads = []
+    pos = 0
+    while pos < PC:
+        rem = PC - pos
+        if PAIR == 1 and rem <= 2:
+            loads.append((pos, 2, pos * 4)); pos += 2
+        elif PAIR == 2 and rem == 1:
+            loads.append((pos, 1, pos * 8)); pos += 1
+        else:
+            loads.append((pos, per_vec, pos * 4 * PAIR)); pos += per_vec
+    loads_a = []
+    if PAIR == 1:
+        c = -PADL
+        while c < PC - PADL:
+            rem = PC - PADL - c
+            n = 4 if (c % 4 == 0 and rem >= 4) else 2 if (c % 2 == 0 and rem >= 2) else 1
+            loads_a.append((c + PADL, n, c * 4))
+            c += n
+    return loads, loads_a, pos, PADL
+
+
+def sieve_layout(OT, KH, KW):
+    """bit position of handler (o, kh, kw): whole output channels per 32-bit mask word"""
+    OPW = max(1, 32 // (KH * KW))
+    NW = (OT + OPW - 1) // OPW
+    return OPW, NW
+
+
+def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b"):
+    assert PAIR == 1
+    NACC = OT * TY * TX
+    PR = (TY - 1) * S + KH
+    PC = (TX - 1) * S + KW
+    loads, loads_a, XW, PADL = load_plans(PC, PAIR, KW)
+    NX = PR * XW
+    NC = OT * KH * KW
+    OPW, NW = sieve_layout(OT, KH, KW)
+    HB = 4 * (1 + NW)                 # header bytes: {plane offset | END, mask words}
+    NOPS = NACC
+    L = []
+    a = L.append
+    a("{")
+    a(".reg .f32 x<%d>, w, wn;" % NX)
+    a(".reg .b32 pc, off, noff, t, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
+    a(".reg .pred p;")
+    # Stream (4-byte words): H_0 | H_1 W_0.. | H_2 W_1.. | ... | H_END W_(n-1).. ; H = {plane byte offset, masks};
+    # the header of step i+1 precedes the weights of step i, so it is fetched a whole step ahead.
+    a("mov.u32 pc, %%%d;" % NOPS)
+    a("ld.shared.b32 off, [pc];")
+    for k in range(NW):
+        a("ld.shared.b32 m%d, [pc+%d];" % (k, 4 + 4 * k))
+    # every lane holds the same header; the broadcast shuffles only tell ptxas so (uniform registers, BRA.U without
+    # BSSY/BSYNC reconvergence bookkeeping around every skip)
+    a("shfl.sync.idx.b32 off, off, 0, 0x1f, 0xffffffff;")
+    for k in range(NW):
+        a("shfl.sync.idx.b32 m%d, m%d, 0, 0x1f, 0xffffffff;" % (k, k))
+    a("add.u32 pc, pc, %d;" % HB)
+    a("SLOOP:")
+    a("setp.eq.u32 p, off, 0xffffffff;")
+    a("@p bra.uni SDONE;")
+    a("ld.shared.b32 noff, [pc];")
+    for k in range(NW):
+        a("ld.shared.b32 nm%d, [pc+%d];" % (k, 4 + 4 * k))
+    a("ld.shared.f32 wn, [pc+%d];" % HB)
+    a("add.u32 pc, pc, %d;" % HB)      # pc -> the weight held in wn
+    a("shfl.sync.idx.b32 noff, noff, 0, 0x1f, 0xffffffff;")   # warp-uniform early: consumed at the end of the step
+    for k in range(NW):
+        a("shfl.sync.idx.b32 nm%d, nm%d, 0, 0x1f, 0xffffffff;" % (k, k))
+    a("add.u32 ad0, %%%d, off;" % (NOPS + 1))
+    for r in range(1, PR):
+        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
+
+    def emit_loads(plan):
+        for r in range(PR):
+            for (po, cnt, byte) in plan:
+                b = r * XW + po
+                sgn = "+%d" % byte
+                if cnt == 4:
+                    a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+                elif cnt == 2:
+                    a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+                else:
+                    a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+    emit_loads(loads_a if PLAN == "a" else loads)
+    for o in range(OT):
+        wd, ob = o // OPW, (o % OPW) * KH * KW
+        if KH * KW > 1:
+            a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << (KH * KW)) - 1) << ob))
+            a("setp.eq.u32 p, t, 0;")
+            a("@p bra.uni SO%dE;" % o)
+        for kh in range(KH):
+            if KW > 1 and KH > 1:
+                a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << KW) - 1) << (ob + kh * KW)))
+                a("setp.eq.u32 p, t, 0;")
+                a("@p bra.uni SR%d_%dE;" % (o, kh))
+            for kw in range(KW):
+                c = (o * KH + kh) * KW + kw
+                a("and.b32 t, m%d, 0x%x;" % (wd, 1 << (ob + kh * KW + kw)))
+                a("setp.eq.u32 p, t, 0;")
+                a("@p bra.uni SH%dE;" % c)
+                a("mov.f32 w, wn;")
+                a("ld.shared.f32 wn, [pc+4];")
+                a("add.u32 pc, pc, 4;")
+                for ty in range(TY):
+                    for tx in range(TX):
+                        acc = (o * TY + ty) * TX + tx
+                        xi = (ty * S + kh) * XW + tx * S + kw
+                        a("fma.rn.f32 %%%d, w, x%d, %%%d;" % (acc, xi, acc))
+                a("SH%dE:" % c)
+            if KW > 1 and KH > 1:
+                a("SR%d_%dE:" % (o, kh))
+        if KH * KW > 1:
+            a("SO%dE:" % o)
+    a("mov.b32 off, noff;")
+    for k in range(NW):
+        a("mov.b32 m%d, nm%d;" % (k, k))
+    a("bra.uni SLOOP;")
+    a("SDONE:")
+    a("}")
+    body = "\n".join('      "%s\\n\\t"' % s for s in L)
+    ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
+    name = "s%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, OT, TY, TX, KH, KW, S, NCW, "_r%d" % CREGS if CREGS else "")
+    src = []
+    src.append("// ---- sieve variant %s: %d accumulator registers, %d patch registers, %d handlers, %d mask words ----"
+               % (name, NACC, NX, NC, NW))
+    src.append("template <> struct Interp<%d> {" % vid)
+    src.append("  static constexpr int OT = %d, TY = %d, TX = %d, KH = %d, KW = %d, S = %d, PAIR = %d;"
+               % (OT, TY, TX, KH, KW, S, PAIR))
+    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;" % (NOPS, NC, PR, PC, XW, PADL))
+    NTW = NCW + (4 if CREGS else NLW)
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;" % (NCW, NLW, NTW, CREGS, 1 if PLAN == "a" else 2))
+    src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
+    src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
+    src.append("                                             unsigned pitch_bytes, unsigned /*plan_a*/) {")
+    src.append("    asm volatile(")
+    src.append(body)
+    src.append("      : %s" % ops_out)
+    src.append('      : "r"(prog), "r"(lane_base), "r"(pitch_bytes)')
+    src.append('      : "memory");')
+    src.append("  }")
+    src.append("};")
+    return "\n".join(src)
+
+
+# ---- fourth generation ("rows"): the unit of control flow is a kernel ROW (oc_local, kh).  Empty rows are skipped
+# with a warp-uniform direct branch; inside a nonempty row the KW taps are straight-line code, each FMA guarded by
+# a predicate (absent taps issue but do not execute).  A taken branch costs ~50 cycles of front-end redirect, a
+# predicated-off instruction one issue slot, so this trades redirects for issue slots -- which the packed
+# fma.rn.f32x2 (PAIR 2: two images per lane) has to spare: 2 FMAs per lane per slot.
+# Stream (16-byte quads): H_0 | H_1 R_0.. | H_2 R_1.. | ... | H_END R_(n-1).. ; H = {plane byte offset | END, mask
+# words, pad}, R = the KW weights of one nonempty row (zeros for absent taps), rows in (oc_local, kh) order.
+# tuple: (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN, TAP)  TAP: "p" predicated, "j" branch per tap, "d" dense
+ROWS = [
+    # 3x3, two images per lane (FFMA2), patch-aligned rows
+    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),    # 56
+    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "j"),
+    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "d"),
+    (2, 4, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),
+    (4, 2, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),   # 60
+    (5, 2, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),
+    (8, 2, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),
+    (6, 2, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),
+    # 3x3, one image per lane
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", "p"),    # 64
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", "p"),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a", "p"),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", "p"),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", "d"),    # 68
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", "p"),
+    # 5x5
+    (4, 2, 4, 5, 5, 1, 2, 8, 4, 232, "b", "p"),    # 70
+    (2, 4, 4, 5, 5, 1, 2, 8, 4, 232, "b", "p"),
+    (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", "p"),
+    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "b", "p"),
+    # 3x3 stride 2
+    (4, 2, 4, 3, 3, 2, 2, 8, 4, 232, "b", "p"),    # 74
+]
+
+
+def rows_layout(OT, KH, KW):
+    OPW, NW = sieve_layout(OT, KH, KW)
+    HQ = 1 if NW <= 3 else 2          # header quads
+    WQ = 1 if KW <= 4 else 2          # quads per row of weights
+    return OPW, NW, HQ, WQ
+
+
+def gen_rows(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN, TAP):
+    NACC = OT * TY * TX
+    PR = (TY - 1) * S + KH
+    PC = (TX - 1) * S + KW
+    loads, loads_a, XW, PADL = load_plans(PC, PAIR, KW)
+    assert PLAN == "b" or PAIR == 1
+    NX = PR * XW
+    NC = OT * KH * KW
+    OPW, NW, HQ, WQ = rows_layout(OT, KH, KW)
+    HB, WB = 16 * HQ, 16 * WQ
+    NOPS = NACC * PAIR
+    L = []
+    a = L.append
+    a("{")
+    if PAIR == 1:
+        a(".reg .f32 x<%d>, ww<%d>;" % (NX, KW))
+    else:
+        a(".reg .b64 x<%d>, a<%d>, ww<%d>;" % (NX, NACC, KW))
+        for i in range(NACC):
+            a("mov.b64 a%d, {%%%d, %%%d};" % (i, 2 * i, 2 * i + 1))
+    a(".reg .f32 wn<%d>;" % (4 * WQ))
+    # m<k>: warp-uniform copies of the mask words (row / channel branches); mv<k>: the same words as plain per-lane
+    # registers for the tap predicates -- a predicate ptxas can prove uniform is turned back into a branch
+    # (loaded through an address ptxas cannot prove uniform: pc + (lane_base >> 31), the shift is always 0)
+    a(".reg .b32 pc, pcl, off, t, ad<%d>, m<%d>, mv<%d>, nv<%d>, nh<%d>, nu<%d>;" % (PR, NW, NW, 4 * HQ, 4 * HQ, NW + 1))
+    a("shr.u32 pcl, %%%d, 31;" % (NOPS + 1))
+    a(".reg .pred p, q<%d>;" % KW)
+
+    def ld_quads(regs, base, nq, ptr="pc"):
+        for k in range(nq):
+            a("ld.shared.v4.b32 {%s}, [%s+%d];" % (", ".join("%s%d" % (regs, 4 * k + j) for j in range(4)), ptr, base + 16 * k))
+
+    def ld_quads_f(regs, base, nq):
+        for k in range(nq):
+            a("ld.shared.v4.f32 {%s}, [pc+%d];" % (", ".join("%s%d" % (regs, 4 * k + j) for j in range(4)), base + 16 * k))
+    a("mov.u32 pc, %%%d;" % NOPS)
+    a("add.u32 pcl, pcl, pc;")
+    ld_quads("nh", 0, HQ)
+    if TAP == "p":
+        ld_quads("nv", 0, HQ, "pcl")
+    a("shfl.sync.idx.b32 off, nh0, 0, 0x1f, 0xffffffff;")
+    for k in range(NW):
+        a("shfl.sync.idx.b32 m%d, nh%d, 0, 0x1f, 0xffffffff;" % (k, k + 1))
+        if TAP == "p":
+            a("mov.b32 mv%d, nv%d;" % (k, k + 1))
+    a("add.u32 pc, pc, %d;" % HB)
+    a("add.u32 pcl, pcl, %d;" % HB)
+    a("RLOOP:")
+    a("setp.eq.u32 p, off, 0xffffffff;")
+    a("@p bra.uni RDONE;")
+    ld_quads("nh", 0, HQ)
+    if TAP == "p":
+        ld_quads("nv", 0, HQ, "pcl")
+    ld_quads_f("wn", HB, WQ)
+    a("add.u32 pc, pc, %d;" % HB)
+    a("add.u32 pcl, pcl, %d;" % HB)
+    a("add.u32 ad0, %%%d, off;" % (NOPS + 1))
+    for r in range(1, PR):
+        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
+    plan = loads_a if PLAN == "a" else loads
+    for r in range(PR):
+        for (po, cnt, byte) in plan:
+            b = r * XW + po
+            sgn = "+%d" % byte
+            if PAIR == 1 and cnt == 4:
+                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+            elif PAIR == 1 and cnt == 2:
+                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+            elif PAIR == 1:
+                a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+            elif cnt == 2:
+                a("ld.shared.v2.b64 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+            else:
+                a("ld.shared.b64 x%d, [ad%d%s];" % (b, r, sgn))
+    # the next header, made warp-uniform early (it is only consumed at the end of the step)
+    for k in range(NW + 1):
+        a("shfl.sync.idx.b32 nu%d, nh%d, 0, 0x1f, 0xffffffff;" % (k, k))
+    for o in range(OT):
+        wd, ob = o // OPW, (o % OPW) * KH * KW
+        if KH > 1:
+            a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << (KH * KW)) - 1) << ob))
+            a("setp.eq.u32 p, t, 0;")
+            a("@p bra.uni RO%dE;" % o)
+        for kh in range(KH):
+            a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << KW) - 1) << (ob + kh * KW)))
+            a("setp.eq.u32 p, t, 0;")
+            a("@p bra.uni RR%d_%dE;" % (o, kh))
+            for kw in range(KW):
+                if PAIR == 1:
+                    a("mov.f32 ww%d, wn%d;" % (kw, kw))
+                else:
+                    a("mov.b64 ww%d, {wn%d, wn%d};" % (kw, kw, kw))
+            ld_quads_f("wn", WB, WQ)
+            a("add.u32 pc, pc, %d;" % WB)
+            a("add.u32 pcl, pcl, %d;" % WB)
+            for kw in range(KW):
+                c = (o * KH + kh) * KW + kw
+                guard = ""
+                if TAP in ("p", "j"):
+                    a("and.b32 t, %s%d, 0x%x;" % ("mv" if TAP == "p" else "m", wd, 1 << (ob + kh * KW + kw)))
+                    a("setp.ne.u32 q%d, t, 0;" % kw)
+                if TAP == "j":
+                    a("@!q%d bra.uni RT%dE;" % (kw, c))
+                elif TAP == "p":
+                    guard = "@q%d " % kw
+                for ty in range(TY):
+                    for tx in range(TX):
+                        acc = (o * TY + ty) * TX + tx
+                        xi = (ty * S + kh) * XW + tx * S + kw
+                        if PAIR == 1:
+                            a("%sfma.rn.f32 %%%d, ww%d, x%d, %%%d;" % (guard, acc, kw, xi, acc))
+                        else:
+                            a("%sfma.rn.f32x2 a%d, ww%d, x%d, a%d;" % (guard, acc, kw, xi, acc))
+                if TAP == "j":
+                    a("RT%dE:" % c)
+            a("RR%d_%dE:" % (o, kh))
+        if KH > 1:
+            a("RO%dE:" % o)
+    a("mov.b32 off, nu0;")
+    for k in range(NW):
+        a("mov.b32 m%d, nu%d;" % (k, k + 1))
+        if TAP == "p":
+            a("mov.b32 mv%d, nv%d;" % (k, k + 1))
+    a("bra.uni RLOOP;")
+    a("RDONE:")
+    if PAIR == 2:
+        for i in range(NACC):
+            a("mov.b64 {%%%d, %%%d}, a%d;" % (2 * i, 2 * i + 1, i))
+    a("}")
+    body = "\n".join('      "%s\\n\\t"' % s for s in L)
+    ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
+    name = "r%s%s_o%d_y%d_x%d_k%dx%d_s%d_p%d_w%d%s" % (PLAN, TAP, OT, TY, TX, KH, KW, S, PAIR, NCW,
+                                                      "_r%d" % CREGS if CREGS else "")
+    src = []
+    src.append("// ---- rows variant %s: %d accumulator registers, %d patch registers%s, %d rows, %d mask words ----"
+               % (name, NOPS, NX * PAIR, "" if PAIR == 1 else " (64-bit pairs)", OT * KH, NW))
+    src.append("template <> struct Interp<%d> {" % vid)
+    src.append("  static constexpr int OT = %d, TY = %d, TX = %d, KH = %d, KW = %d, S = %d, PAIR = %d;"
+               % (OT, TY, TX, KH, KW, S, PAIR))
+    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;" % (NOPS, NC, PR, PC, XW, PADL))
+    NTW = NCW + (4 if CREGS else NLW)
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;"
+               % (NCW, NLW, NTW, CREGS, 3 if PLAN == "a" else 4))
+    src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
+    src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
+    src.append("                                             unsigned pitch_bytes, unsigned /*plan_a*/) {")
+    src.append("    asm volatile(")
+    src.append(body)
+    src.append("      : %s" % ops_out)
+    src.append('      : "r"(prog), "r"(lane_base), "r"(pitch_bytes)')
+    src.append('      : "memory");')
+    src.append("  }")
+    src.append("};")
+    return "\n".join(src)
+
+
 def gen_variant(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0):
     NACC = OT * TY * TX               # accumulator registers (32-bit for PAIR 1, 64-bit pairs for PAIR 2)
     PR = (TY - 1) * S + KH            # patch rows held in registers
@@ -184,11 +566,11 @@ def gen_variant(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0):
     # CREGS > 0: the loader warps form a warpgroup of their own (4 warps, NLW of them active) that gives its
     # registers back with setmaxnreg.dec and the compute warpgroups grow to CREGS with setmaxnreg.inc
     NTW = NCW + (4 if CREGS else NLW)
-    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d;" % (NCW, NLW, NTW, CREGS))
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = 0;" % (NCW, NLW, NTW, CREGS))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base,"
                % NOPS)
-    src.append("                                             unsigned pitch_bytes) {")
+    src.append("                                             unsigned pitch_bytes, unsigned /*plan_a*/) {")
     src.append("    asm volatile(")
     src.append(body)
     src.append("      : %s" % ops_out)
@@ -207,25 +589,27 @@ def main():
             "// offset of the channel plane), NC+2: end of segment.",
             "#pragma once",
             "template <int VID> struct Interp;"]
-    for i, v in enumerate(VARIANTS):
+    ALL = ([(v, 0) for v in VARIANTS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE] +
+           [(v, 3 if v[10] == "a" else 4) for v in ROWS])
+    for i, (v, mode) in enumerate(ALL):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
-        txt = "\n".join(head + [gen_variant(i, *v)]) + "\n"
+        txt = "\n".join(head + [(gen_variant, gen_sieve, gen_sieve, gen_rows, gen_rows)[mode](i, *v)]) + "\n"
         if not os.path.exists(path) or open(path).read() != txt:
             open(path, "w").write(txt)
     lst = os.path.join(OUTDIR, "variant_list.inc")
-    txt = "// GENERATED by tools/gen_interp.py\n#define ESCORT_NUM_VARIANTS %d\n#define ESCORT_VARIANT_LIST(X) \\\n" % len(VARIANTS)
-    def row(i, v):
+    txt = "// GENERATED by tools/gen_interp.py\n#define ESCORT_NUM_VARIANTS %d\n#define ESCORT_VARIANT_LIST(X) \\\n" % len(ALL)
+    def row(i, v, mode):
         cregs = v[9] if len(v) > 9 else 0
         ntw = v[7] + (4 if cregs else v[8])
-        return "  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + tuple(v[:9]) + (ntw,))
-    txt += " \\\n".join(row(i, v) for i, v in enumerate(VARIANTS)) + "\n"
+        return "  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + tuple(v[:9]) + (ntw, mode))
+    txt += " \\\n".join(row(i, v, mode) for i, (v, mode) in enumerate(ALL)) + "\n"
     if not os.path.exists(lst) or open(lst).read() != txt:
         open(lst, "w").write(txt)
-    print("generated %d variants in %s" % (len(VARIANTS), OUTDIR))
+    print("generated %d variants in %s" % (len(ALL), OUTDIR))
 
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--count":
-        print(len(VARIANTS))
+        print(len(VARIANTS) + len(SIEVE) + len(ROWS))
     else:
         main()

@@ -13,8 +13,13 @@ torch.zeros(1).cuda()
 lib = capi.lib
 lib.escort_interp_bench.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int)]
-per_loads = [int(a) for a in sys.argv[1:]] or [0, 16, 6]
+# python tools/interp_bench.py [--from V] [per_load ...]; for the sieve variants per_load = density in percent
+args = sys.argv[1:]
 v = 1
+if args and args[0] == "--from":
+    v = int(args[1])
+    args = args[2:]
+per_loads = [int(a) for a in args] or [0, 16, 6]
 while True:
     row = []
     for pl in per_loads:

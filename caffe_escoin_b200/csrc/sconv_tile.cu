@@ -215,17 +215,25 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int XW = PAIR == 2 ? PC : (PC % 4 == 0 ? PC : (PC % 4 <= 2 ? PC - PC % 4 + 2 : PC - PC % 4 + 4));
   // TMA staging (cp.async.bulk.tensor with out-of-bounds zero fill = the halo) needs 16-byte global strides and a
   // 16-byte aligned innermost start coordinate, hence the aligned-body row layout
-  // (sieve variants are compiled for one patch-load plan: MODE 1 = aligned body = TMA rows, MODE 2 = patch aligned)
-  const bool use_tma = PAIR == 1 && g.width % 4 == 0 && g.pad_w == (KW - 1) / 2 && tma_encoder() != nullptr &&
-                       !getenv("ESCORT_NO_TMA") && V.MODE != 2 && V.MODE != 4;
+  // (sieve / rows variants are compiled for one patch-load plan: MODE 1, 3 = aligned body, MODE 2, 4 = patch aligned)
+  const bool tma_ok = PAIR == 1 && g.width % 4 == 0 && g.pad_w == (KW - 1) / 2 && tma_encoder() != nullptr &&
+                      !getenv("ESCORT_NO_TMA");
+  const bool plan_b_variant = V.MODE == 2 || V.MODE == 4;
+  // patch-aligned rows cannot come from TMA: a box starting at x = -pad_w faults (illegal instruction, measured on
+  // B200) -- the innermost start coordinate must keep the global address 16-byte aligned, hence the aligned-body
+  // layout for TMA and the cp.async loader for patch-aligned rows
+  const bool use_tma_b = false;
+  const bool use_tma = (tma_ok && !plan_b_variant) || use_tma_b;
   if ((V.MODE == 1 || V.MODE == 3) && !use_tma) return 0;
-  // PAIR 1: data column 0 sits on a 16-byte boundary, HL halo columns to its left (aligned-body layout: TMA and the
-  // lanes' 128-bit loads both need it); PAIR 2: the halo is exactly pad_w positions wide.
-  const int PADL = use_tma ? (KW - 1) / 2 : 0;
-  const int HL = use_tma ? (g.pad_w > 0 ? 4 : 0) : g.pad_w;
-  const int lane_col0 = use_tma ? HL : 0;
+  // aligned body (PAIR 1, TMA): data column 0 sits on a 16-byte boundary, HL = 4 halo columns to its left and the
+  // lane base is the tile's first output column; patch aligned: the halo is exactly pad_w positions wide and the lane
+  // base is the patch's first column
+  const bool aligned_body = use_tma && !use_tma_b;
+  const int PADL = aligned_body ? (KW - 1) / 2 : 0;
+  const int HL = aligned_body ? (g.pad_w > 0 ? 4 : 0) : g.pad_w;
+  const int lane_col0 = aligned_body ? HL : 0;
   // every lane's reads stay inside its row; the pitch keeps 16-byte alignment of every row start
-  const int Pmin = ceil_div(std::max(lane_col0 + (PX - 1) * TX * S + (use_tma ? PC - PADL : XW), HL + g.width + g.pad_w), per_vec) * per_vec;
+  const int Pmin = ceil_div(std::max(lane_col0 + (PX - 1) * TX * S + (aligned_body ? PC - PADL : XW), HL + g.width + g.pad_w), per_vec) * per_vec;
   int dev = 0, max_smem = 0, num_sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -461,7 +469,8 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
                   words.push_back(wv.first);
                 }
               }
-              words.push_back(0u);  // the weight prefetch reads one word past the last weight
+              words.push_back(0u);  // the weight prefetch reads two words past the last weight
+              words.push_back(0u);
               continue;
             }
             if (blk < nblk) {

@@ -157,7 +157,11 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
   constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = IP::NTW * 32;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the broadcast tells ptxas that wid is warp-uniform: everything derived from it (the byte-code segment address,
+  // hence every header word loaded from it) is then uniform too, and the skip branches of the sieve / rows variants
+  // compile to plain branches without per-step SHFL + R2UR or BSSY/BSYNC reconvergence bookkeeping
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
 
   // one-time set-up: barriers, zero halo (all stages), loader scatter table

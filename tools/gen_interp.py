@@ -102,6 +102,16 @@ SIEVE = [
     (4, 4, 4, 3, 3, 2, 1, 8, 4, 232, "b"),    # 53
     (8, 2, 4, 3, 3, 2, 1, 12, 4, 152, "b"),
 ]
+# rolling-row-predicate editions (appended after ROWS so earlier ids stay put)
+SIEVE_R = [
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a", 1),   # 75
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", 1),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", 1),
+    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 79
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
+    (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
+]
 
 
 def load_plans(PC, PAIR, KW):
@@ -135,7 +145,7 @@ def sieve_layout(OT, KH, KW):
     return OPW, NW
 
 
-def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b"):
+def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROLL=0):
     assert PAIR == 1
     NACC = OT * TY * TX
     PR = (TY - 1) * S + KH
@@ -143,83 +153,129 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b"):
     loads, loads_a, XW, PADL = load_plans(PC, PAIR, KW)
     NX = PR * XW
     NC = OT * KH * KW
+    NR = OT * KH                      # kernel rows (oc_local, kh)
     OPW, NW = sieve_layout(OT, KH, KW)
     HB = 4 * (1 + NW)                 # header bytes: {plane offset | END, mask words}
     NOPS = NACC
     L = []
     a = L.append
     a("{")
-    a(".reg .f32 x<%d>, w, wn;" % NX)
-    a(".reg .b32 pc, off, noff, t, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
-    a(".reg .pred p;")
+    a(".reg .f32 x<%d>, w, wn, wn2;" % NX)
+    a(".reg .b32 pc, pw, off, noff, t, t2, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
+    a(".reg .pred p, pr<3>, pt<%d>;" % KW)
     # Stream (4-byte words): H_0 | H_1 W_0.. | H_2 W_1.. | ... | H_END W_(n-1).. ; H = {plane byte offset, masks};
     # the header of step i+1 precedes the weights of step i, so it is fetched a whole step ahead.
+    # pc walks the headers and stays provably warp-uniform (advanced by the popcount of the masks), so the masks end
+    # up in uniform registers and every skip is a BRA.U.  pw walks the weights; it is pc + (lane_base >> 31), i.e. the
+    # same address, but not provably uniform: otherwise ptxas routes every weight LDS -> R2UR -> FFMA(UR) and the
+    # conversion sits on the critical path of each tap.  Weights are prefetched two taps ahead (w <- wn <- wn2 <- LDS).
     a("mov.u32 pc, %%%d;" % NOPS)
+    a("shr.u32 pw, %%%d, 31;" % (NOPS + 1))
+    a("add.u32 pw, pw, pc;")
     a("ld.shared.b32 off, [pc];")
     for k in range(NW):
         a("ld.shared.b32 m%d, [pc+%d];" % (k, 4 + 4 * k))
-    # every lane holds the same header; the broadcast shuffles only tell ptxas so (uniform registers, BRA.U without
-    # BSSY/BSYNC reconvergence bookkeeping around every skip)
+    # every lane holds the same header; the broadcast shuffles only tell ptxas so when it cannot prove it itself
     a("shfl.sync.idx.b32 off, off, 0, 0x1f, 0xffffffff;")
     for k in range(NW):
         a("shfl.sync.idx.b32 m%d, m%d, 0, 0x1f, 0xffffffff;" % (k, k))
     a("add.u32 pc, pc, %d;" % HB)
+    a("add.u32 pw, pw, %d;" % HB)
     a("SLOOP:")
     a("setp.eq.u32 p, off, 0xffffffff;")
     a("@p bra.uni SDONE;")
     a("ld.shared.b32 noff, [pc];")
     for k in range(NW):
         a("ld.shared.b32 nm%d, [pc+%d];" % (k, 4 + 4 * k))
-    a("ld.shared.f32 wn, [pc+%d];" % HB)
-    a("add.u32 pc, pc, %d;" % HB)      # pc -> the weight held in wn
-    a("shfl.sync.idx.b32 noff, noff, 0, 0x1f, 0xffffffff;")   # warp-uniform early: consumed at the end of the step
+    a("ld.shared.f32 wn, [pw+%d];" % HB)
+    a("ld.shared.f32 wn2, [pw+%d];" % (HB + 4))
+    a("add.u32 pw, pw, %d;" % HB)      # pw -> the weight held in wn
+    # pc -> header of step i+2 = past this step's weights
+    a("popc.b32 t, m0;")
+    for k in range(1, NW):
+        a("popc.b32 t2, m%d;" % k)
+        a("add.u32 t, t, t2;")
+    a("shl.b32 t, t, 2;")
+    a("add.u32 pc, pc, t;")
+    a("add.u32 pc, pc, %d;" % HB)
+    a("shfl.sync.idx.b32 noff, noff, 0, 0x1f, 0xffffffff;")
     for k in range(NW):
         a("shfl.sync.idx.b32 nm%d, nm%d, 0, 0x1f, 0xffffffff;" % (k, k))
+
+    def rowmask(r):
+        o, kh = r // KH, r % KH
+        return o // OPW, ((1 << KW) - 1) << ((o % OPW) * KH * KW + kh * KW)
+
+    def set_row_pred(r):
+        wd, msk = rowmask(r)
+        a("and.b32 t, m%d, 0x%x;" % (wd, msk))
+        a("setp.ne.u32 pr%d, t, 0;" % (r % 3))
+    if ROLL:
+        # rolling row predicates, two rows ahead of their branch (a predicate consumed right after it is produced
+        # stalls the branch for the uniform-datapath latency)
+        set_row_pred(0)
+        if NR > 1:
+            set_row_pred(1)
     a("add.u32 ad0, %%%d, off;" % (NOPS + 1))
     for r in range(1, PR):
         a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
+    plan = loads_a if PLAN == "a" else loads
+    for r in range(PR):
+        for (po, cnt, byte) in plan:
+            b = r * XW + po
+            sgn = "+%d" % byte
+            if cnt == 4:
+                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+            elif cnt == 2:
+                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+            else:
+                a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
 
-    def emit_loads(plan):
-        for r in range(PR):
-            for (po, cnt, byte) in plan:
-                b = r * XW + po
-                sgn = "+%d" % byte
-                if cnt == 4:
-                    a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
-                elif cnt == 2:
-                    a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
-                else:
-                    a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
-    emit_loads(loads_a if PLAN == "a" else loads)
-    for o in range(OT):
+    def emit_taps(o, kh, single_test_done):
         wd, ob = o // OPW, (o % OPW) * KH * KW
-        if KH * KW > 1:
-            a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << (KH * KW)) - 1) << ob))
-            a("setp.eq.u32 p, t, 0;")
-            a("@p bra.uni SO%dE;" % o)
-        for kh in range(KH):
-            if KW > 1 and KH > 1:
-                a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << KW) - 1) << (ob + kh * KW)))
-                a("setp.eq.u32 p, t, 0;")
-                a("@p bra.uni SR%d_%dE;" % (o, kh))
+        if not single_test_done:
             for kw in range(KW):
-                c = (o * KH + kh) * KW + kw
                 a("and.b32 t, m%d, 0x%x;" % (wd, 1 << (ob + kh * KW + kw)))
+                a("setp.ne.u32 pt%d, t, 0;" % kw)
+        for kw in range(KW):
+            c = (o * KH + kh) * KW + kw
+            if not single_test_done:
+                a("@!pt%d bra.uni SH%dE;" % (kw, c))
+            a("mov.f32 w, wn;")
+            a("mov.f32 wn, wn2;")
+            a("ld.shared.f32 wn2, [pw+8];")
+            a("add.u32 pw, pw, 4;")
+            for ty in range(TY):
+                for tx in range(TX):
+                    acc = (o * TY + ty) * TX + tx
+                    xi = (ty * S + kh) * XW + tx * S + kw
+                    a("fma.rn.f32 %%%d, w, x%d, %%%d;" % (acc, xi, acc))
+            a("SH%dE:" % c)
+    if ROLL:
+        for r in range(NR):
+            a("SRR%d:" % r)
+            if r + 2 < NR:
+                set_row_pred(r + 2)
+            a("@!pr%d bra.uni SRR%d;" % (r % 3, r + 1))
+            emit_taps(r // KH, r % KH, KW == 1)
+        a("SRR%d:" % NR)
+    else:
+        for o in range(OT):
+            wd, ob = o // OPW, (o % OPW) * KH * KW
+            if KH * KW > 1:
+                a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << (KH * KW)) - 1) << ob))
                 a("setp.eq.u32 p, t, 0;")
-                a("@p bra.uni SH%dE;" % c)
-                a("mov.f32 w, wn;")
-                a("ld.shared.f32 wn, [pc+4];")
-                a("add.u32 pc, pc, 4;")
-                for ty in range(TY):
-                    for tx in range(TX):
-                        acc = (o * TY + ty) * TX + tx
-                        xi = (ty * S + kh) * XW + tx * S + kw
-                        a("fma.rn.f32 %%%d, w, x%d, %%%d;" % (acc, xi, acc))
-                a("SH%dE:" % c)
-            if KW > 1 and KH > 1:
-                a("SR%d_%dE:" % (o, kh))
-        if KH * KW > 1:
-            a("SO%dE:" % o)
+                a("@p bra.uni SO%dE;" % o)
+            for kh in range(KH):
+                if KW > 1 and KH > 1:
+                    a("and.b32 t, m%d, 0x%x;" % (wd, ((1 << KW) - 1) << (ob + kh * KW)))
+                    a("setp.eq.u32 p, t, 0;")
+                    a("@p bra.uni SR%d_%dE;" % (o, kh))
+                emit_taps(o, kh, False)
+                if KW > 1 and KH > 1:
+                    a("SR%d_%dE:" % (o, kh))
+            if KH * KW > 1:
+                a("SO%dE:" % o)
     a("mov.b32 off, noff;")
     for k in range(NW):
         a("mov.b32 m%d, nm%d;" % (k, k))
@@ -228,7 +284,8 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b"):
     a("}")
     body = "\n".join('      "%s\\n\\t"' % s for s in L)
     ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
-    name = "s%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, OT, TY, TX, KH, KW, S, NCW, "_r%d" % CREGS if CREGS else "")
+    name = "s%s%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, "r" if ROLL else "", OT, TY, TX, KH, KW, S, NCW,
+                                                  "_r%d" % CREGS if CREGS else "")
     src = []
     src.append("// ---- sieve variant %s: %d accumulator registers, %d patch registers, %d handlers, %d mask words ----"
                % (name, NACC, NX, NC, NW))
@@ -590,7 +647,7 @@ def main():
             "#pragma once",
             "template <int VID> struct Interp;"]
     ALL = ([(v, 0) for v in VARIANTS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE] +
-           [(v, 3 if v[10] == "a" else 4) for v in ROWS])
+           [(v, 3 if v[10] == "a" else 4) for v in ROWS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE_R])
     for i, (v, mode) in enumerate(ALL):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
         txt = "\n".join(head + [(gen_variant, gen_sieve, gen_sieve, gen_rows, gen_rows)[mode](i, *v)]) + "\n"
@@ -610,6 +667,6 @@ def main():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--count":
-        print(len(VARIANTS) + len(SIEVE) + len(ROWS))
+        print(len(VARIANTS) + len(SIEVE) + len(ROWS) + len(SIEVE_R))
     else:
         main()

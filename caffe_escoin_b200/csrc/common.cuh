@@ -68,6 +68,13 @@ struct escort_plan {
   // ---- tile-interpreter forward (sconv_tile.cu) ----
   escort::TilePlan *tile;
   std::vector<escort::Nz> *host_nz;  // kept for re-planning with another variant
+  // ---- backward data through the tile kernel: dX = conv(dY, W^T flipped), a forward plan over the transposed,
+  // 180-degree rotated weights (stride 1 only).  Built on first use; owns only g / nnz / host_nz / d_dense_idx / tile.
+  escort_plan *bwd;
+  int bwd_tried;
+  // ---- backward weight through the tile kernel's "W" variants (stride 1 only), built on first use
+  escort::TilePlan *tile_w;
+  int tile_w_tried;
 };
 
 namespace escort {
@@ -77,6 +84,9 @@ void tile_plan_free(TilePlan *tp);
 int tile_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,
                  cudaStream_t stream);
 int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream);
+int tile_bwdw_build(escort_plan *plan, cudaStream_t stream);
+int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_diff, float *wd_dense, float *wd_csr,
+              int accumulate, cudaStream_t stream);
 const char *tile_kernel_name(const TilePlan *tp);
 int tile_num_variants();
 bool tile_variant_applies(const escort_plan *plan, int variant);  // variant = 1-based index

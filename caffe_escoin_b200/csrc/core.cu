@@ -435,8 +435,64 @@ extern "C" int escort_plan_destroy(escort_plan *p) {
   cudaFree(p->d_tsrc);
   cudaFree(p->d_wmeta);
   if (p->tile) tile_plan_free(p->tile);
+  if (p->tile_w) tile_plan_free(p->tile_w);
+  if (p->bwd) escort_plan_destroy(p->bwd);
   delete p->host_nz;
   delete p;
+  return 0;
+}
+
+// Backward data as a forward convolution (stride 1, no dilation): bottom_diff = conv(top_diff, W'), with
+// W'[ic][oc][kh'][kw'] = W[oc][ic][K-1-kh'][K-1-kw'] and pad' = K-1-pad, so the tile kernel (and its plan-time
+// compiler) serves both directions.  The sub-plan indexes the ORIGINAL dense weight tensor, so escort_refresh_values
+// refreshes it from the same weights.  Returns 0 and leaves p->bwd null when the geometry does not qualify.
+static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
+  p->bwd_tried = 1;
+  const escort_geom &g = p->g;
+  if (g.stride_h != 1 || g.stride_w != 1 || g.dilation_h != 1 || g.dilation_w != 1) return 0;
+  if (g.kernel_h - 1 - g.pad_h < 0 || g.kernel_w - 1 - g.pad_w < 0 || p->nnz == 0) return 0;
+  escort_plan *q = new escort_plan();
+  memset(q, 0, sizeof(*q));
+  q->g = g;
+  q->g.channels = g.num_output;
+  q->g.num_output = g.channels;
+  q->g.height = p->Ho;
+  q->g.width = p->Wo;
+  q->g.pad_h = g.kernel_h - 1 - g.pad_h;
+  q->g.pad_w = g.kernel_w - 1 - g.pad_w;
+  q->Ho = out_dim(q->g.height, q->g.pad_h, g.kernel_h, 1, 1);
+  q->Wo = out_dim(q->g.width, q->g.pad_w, g.kernel_w, 1, 1);
+  if (q->Ho != g.height || q->Wo != g.width) {
+    delete q;
+    return 0;
+  }
+  q->device = p->device;
+  q->nnz = p->nnz;
+  q->variant = -1;
+  q->host_nz = new std::vector<Nz>();
+  q->host_nz->reserve(p->nnz);
+  std::vector<int> dense_idx;
+  dense_idx.reserve(p->nnz);
+  for (const Nz &z : *p->host_nz) {
+    Nz t = z;
+    t.oc = z.ic;
+    t.ic = z.oc;
+    t.kh = g.kernel_h - 1 - z.kh;
+    t.kw = g.kernel_w - 1 - z.kw;
+    q->host_nz->push_back(t);
+    dense_idx.push_back(z.dense_idx);
+  }
+  int rc = upload(&q->d_dense_idx, dense_idx, stream);
+  if (!rc) rc = tile_plan_build(q, -1, stream);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  }
+  if (rc || !q->tile) {
+    escort_plan_destroy(q);
+    return rc;
+  }
+  p->bwd = q;
   return 0;
 }
 
@@ -479,11 +535,11 @@ extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_ra
 }
 
 // Plan-time selection of the forward variant by measurement (the cuDNN "find" idiom): every variant that
-// supports the geometry is built and timed on a zero-filled scratch batch of `num` images on `stream`; the
-// fastest is kept.  Called by the host layer once after WeightAlign; synchronises the stream.
-extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");
+// supports the geometry is built with the planner's favourite tiling and timed on a zero-filled scratch batch of
+// `num` images on `stream`; the three fastest are then re-timed with the runner-up tilings and the best
+// (variant, tiling) is kept.  The backward-data sub-plan (a forward plan over the transposed weights) is tuned the
+// same way.  Called by the host layer once after WeightAlign; synchronises the stream.
+static int autotune_one(escort_plan *p, int num, cudaStream_t stream) {
   const escort_geom &g = p->g;
   const size_t in_elems = (size_t)num * g.channels * g.height * g.width;
   const size_t out_elems = (size_t)num * g.num_output * p->Ho * p->Wo;
@@ -498,28 +554,43 @@ extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t str
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  int best_v = 0;
-  float best_ms = 1e30f;
+  auto time_config = [&](int v, int rank) -> float {
+    if (escort_plan_set_config(p, v, rank) != 0) return -1.f;  // no such layout candidate
+    if (v > 0 && !p->tile) return -1.f;
+    float ms_best = 1e30f;
+    for (int it = 0; it < 3; ++it) {
+      cudaEventRecord(e0, stream);
+      if (escort_sconv_forward(p, num, x, nullptr, 0, y, stream) != 0) return -1.f;
+      cudaEventRecord(e1, stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess) return -1.f;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (it > 0 && ms < ms_best) ms_best = ms;
+    }
+    return ms_best;
+  };
+  std::vector<std::pair<float, int>> first;  // (ms, variant) with the favourite tiling
   const int nvar = tile_num_variants();
-  int best_rank = 0;
-  for (int v = 0; v <= nvar; ++v) {
+  for (int v = (p->d_rowptr ? 0 : 1); v <= nvar; ++v) {  // (a backward sub-plan has no generic kernel)
     if (v > 0 && !tile_variant_applies(p, v)) continue;
-    for (int rank = 0; rank < (v == 0 ? 1 : 4); ++rank) {
-      if (escort_plan_set_config(p, v, rank) != 0) break;  // no such layout candidate
-      if (v > 0 && !p->tile) break;
-      float ms_best = 1e30f;
-      bool ok = true;
-      for (int it = 0; it < 3 && ok; ++it) {
-        cudaEventRecord(e0, stream);
-        ok = escort_sconv_forward(p, num, x, nullptr, 0, y, stream) == 0;
-        cudaEventRecord(e1, stream);
-        if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (it > 0 && ms < ms_best) ms_best = ms;
-      }
-      if (ok && ms_best < best_ms) {
-        best_ms = ms_best;
+    const float ms = time_config(v, 0);
+    if (ms > 0.f) first.push_back({ms, v});
+  }
+  std::sort(first.begin(), first.end());
+  int best_v = 0, best_rank = 0;
+  float best_ms = 1e30f;
+  if (!first.empty()) {
+    best_ms = first[0].first;
+    best_v = first[0].second;
+  }
+  for (size_t i = 0; i < first.size() && i < 3; ++i) {
+    const int v = first[i].second;
+    if (v == 0) continue;
+    for (int rank = 1; rank < 4; ++rank) {
+      const float ms = time_config(v, rank);
+      if (ms < 0.f) break;
+      if (ms < best_ms) {
+        best_ms = ms;
         best_v = v;
         best_rank = rank;
       }
@@ -531,6 +602,26 @@ extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t str
   cudaFree(y);
   cudaGetLastError();
   return escort_plan_set_config(p, best_v, best_rank);
+}
+
+extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");
+  int rc = autotune_one(p, num, stream);
+  if (rc) return rc;
+  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+    rc = build_bwd_plan(p, stream);
+    if (rc) return rc;
+  }
+  if (p->bwd) {
+    rc = autotune_one(p->bwd, num, stream);
+    if (rc) return rc;
+    if (!p->bwd->tile) {  // the generic forward kernel won the sub-plan's timing: keep the dedicated backward kernel
+      escort_plan_destroy(p->bwd);
+      p->bwd = nullptr;
+    }
+  }
+  return 0;
 }
 
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,
@@ -556,6 +647,11 @@ extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *
   ESCORT_REQUIRE(p && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
   if (num == 0) return 0;
   ESCORT_REQUIRE(top_diff && bottom_diff, "escort_sconv_backward_data: null tensor");
+  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+    int rc = build_bwd_plan(p, stream);
+    if (rc) return rc;
+  }
+  if (p->bwd && !getenv("ESCORT_GENERIC_BACKWARD")) return tile_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
   sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
@@ -573,6 +669,14 @@ extern "C" int escort_sconv_backward_weight(escort_plan *p, int num, const float
   ESCORT_REQUIRE(weight_diff_dense || weight_diff_csr, "escort_sconv_backward_weight: no output buffer");
   if (num == 0 || p->nnz == 0) return 0;
   ESCORT_REQUIRE(bottom && top_diff, "escort_sconv_backward_weight: null tensor");
+  if (!p->tile_w && !p->tile_w_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+    p->tile_w_tried = 1;
+    int rc = tile_bwdw_build(p, stream);
+    if (rc) return rc;
+    ESCORT_CUDA(cudaStreamSynchronize(stream));
+  }
+  if (p->tile_w && !getenv("ESCORT_GENERIC_BACKWARD"))
+    return tile_bwdw(p, num, bottom, top_diff, weight_diff_dense, weight_diff_csr, accumulate, stream);
   const escort_geom &g = p->g;
   const int warps = 8;
   const long blocks = (p->nnz + warps - 1) / warps;
@@ -604,6 +708,15 @@ extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense,
   ESCORT_LAUNCH_CHECK();
   refresh_t_kernel<<<blocks, 256, 0, stream>>>(p->nnz, p->d_meta, p->d_tsrc, p->d_tmeta);
   ESCORT_LAUNCH_CHECK();
+  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+    // a refresh means training: build the backward-data sub-plan now, so that it never starts from stale values
+    int rc = build_bwd_plan(p, stream);
+    if (rc) return rc;
+  }
+  if (p->bwd) {
+    int rc = tile_refresh(p->bwd, weights_dense, stream);
+    if (rc) return rc;
+  }
   if (p->tile) return tile_refresh(p, weights_dense, stream);
   return 0;
 }

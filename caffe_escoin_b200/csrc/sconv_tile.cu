@@ -40,12 +40,14 @@ struct VariantDesc {
   const char *name;
   const void *kernel;
   const void *bench;
+  const void *bwdw;
 };
 
 // one translation unit per variant (tile_variant.cu compiled with -DESCORT_VARIANT_ID=k) exports these
 #define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
   const void *tile_variant_kernel_##ID();                         \
   const void *tile_variant_bench_##ID();                          \
+  const void *tile_variant_bwdw_##ID();                           \
   const char *tile_variant_name_##ID();
 ESCORT_VARIANT_LIST(ESCORT_VARIANT_DECL)
 static constexpr int kNumVariants = ESCORT_NUM_VARIANTS;
@@ -54,7 +56,7 @@ static const VariantDesc *variants() {
   static bool init = false;
   if (!init) {
 #define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
-  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID()};
+  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID(), tile_variant_bwdw_##ID()};
     ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
     init = true;
   }
@@ -98,6 +100,7 @@ void tile_plan_free(TilePlan *tp) {
   cudaFree(tp->d_prog);
   cudaFree(tp->d_rtab);
   cudaFree(tp->d_prog_pos);
+  cudaFree(tp->d_tapidx);
   delete tp;
 }
 
@@ -107,43 +110,71 @@ bool tile_variant_applies(const escort_plan *plan, int variant) {
   if (variant < 1 || variant > kNumVariants) return false;
   const VariantDesc &v = kVariants[variant - 1];
   const escort_geom &g = plan->g;
-  return v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h && g.stride_h == g.stride_w &&
+  return v.MODE < 5 && v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h && g.stride_h == g.stride_w &&
          g.dilation_h == 1 && g.dilation_w == 1;
 }
-
 // Pick the default variant for a geometry (auto mode, no autotune); returns -1 if the tile kernel does not apply.
 // The preference lists come from the B200 sweeps in profiles/ (escort_plan_autotune measures instead of guessing).
-static int choose_variant(const escort_geom &g, double density) {
-  struct Pref { int KH, S, OT, TY, TX, PAIR, NCW; };
-  static const Pref prefs[] = {
-      {3, 1, 2, 7, 4, 1, 12}, {3, 1, 4, 7, 4, 1, 8}, {3, 1, 2, 4, 4, 1, 16},
-      {5, 1, 4, 4, 4, 1, 10}, {5, 1, 4, 2, 4, 2, 6},
-      {1, 1, 8, 2, 4, 1, 16}, {3, 2, 8, 2, 4, 1, 14},
-  };
-  const bool low_density = density < 0.18;  // few records per patch load: image-paired FFMA2 amortises best
-  if (low_density && g.kernel_h == 3 && g.stride_h == 1)
-    for (int i = 0; i < kNumVariants; ++i) {
-      const VariantDesc &v = kVariants[i];
-      if (v.KH == 3 && v.KW == 3 && v.S == 1 && v.OT == 4 && v.TY == 4 && v.TX == 4 && v.PAIR == 2 && v.NCW == 8) return i;
-    }
-  for (const Pref &p : prefs)
-    for (int i = 0; i < kNumVariants; ++i) {
-      const VariantDesc &v = kVariants[i];
-      if (v.KH != g.kernel_h || v.KW != g.kernel_w || v.S != g.stride_h) continue;
-      if (v.KH == p.KH && v.S == p.S && v.OT == p.OT && v.TY == p.TY && v.TX == p.TX && v.PAIR == p.PAIR && v.NCW == p.NCW)
-        return i;
+static int find_variant(const char *name) {
+  for (int i = 0; i < kNumVariants; ++i)
+    if (strcmp(kVariants[i].name, name) == 0) return i;
+  return -1;
+}
+typedef CUresult (*TmaEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmaEncodeFn tma_encoder();
+static int choose_variant(const escort_geom &g, double density, int Ho) {
+  const int k = g.kernel_h, s = g.stride_h;
+  const bool tma_w = g.width % 4 == 0 && g.pad_w == (k - 1) / 2 && tma_encoder() != nullptr && !getenv("ESCORT_NO_TMA");
+  const char *prefs[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (k == 3 && g.kernel_w == 3 && s == 1) {
+    if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_sar_o3_y7_x4_k3x3_s1_w12_r152";
+    else if (Ho >= 14) prefs[0] = "sconv_tile_sb_o3_y7_x4_k3x3_s1_w12_r152";
+    else if (density < 0.2) prefs[0] = "sconv_tile_sbr_o4_y4_x4_k3x3_s1_w12_r152";
+    else prefs[0] = "sconv_tile_sb_o6_y4_x4_k3x3_s1_w12_r152";
+    prefs[1] = "sconv_tile_sb_o4_y4_x4_k3x3_s1_w12_r152";
+  } else if (k == 5 && g.kernel_w == 5 && s == 1) {
+    prefs[0] = "sconv_tile_sb_o4_y4_x4_k5x5_s1_w12_r152";
+  } else if (k == 1 && g.kernel_w == 1 && s == 1) {
+    prefs[0] = Ho >= 14 ? "sconv_tile_sb_o6_y7_x4_k1x1_s1_w8_r232" : "sconv_tile_sb_o8_y2_x4_k1x1_s1_w16_r104";
+  } else if (k == 3 && g.kernel_w == 3 && s == 2) {
+    prefs[0] = "sconv_tile_sb_o4_y4_x4_k3x3_s2_w8_r232";
+  }
+  for (const char *p : prefs)
+    if (p) {
+      const int i = find_variant(p);
+      if (i >= 0) return i;
     }
   for (int i = 0; i < kNumVariants; ++i) {
     const VariantDesc &v = kVariants[i];
-    if (v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h) return i;
+    if (v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h && (v.MODE == 0 || v.MODE == 2 || v.MODE == 4)) return i;  // (never a W variant)
   }
   return -1;
 }
 
+// default backward-weight ("W") variant for a geometry, 1-based; 0 if none applies
+int tile_bwdw_variant(const escort_plan *plan) {
+  const escort_geom &g = plan->g;
+  if (g.stride_h != 1 || g.stride_w != 1 || g.dilation_h != 1 || g.dilation_w != 1) return 0;
+  const int k = g.kernel_h;
+  const bool tma_w = g.width % 4 == 0 && g.pad_w == (k - 1) / 2 && tma_encoder() != nullptr && !getenv("ESCORT_NO_TMA");
+  const double density = (double)plan->nnz / ((double)g.num_output * (g.channels / g.group) * g.kernel_h * g.kernel_w);
+  const char *pref = nullptr;
+  if (k == 3 && g.kernel_w == 3) {
+    if (plan->Ho >= 14) pref = tma_w ? "sconv_tile_wa_o3_y7_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o3_y7_x4_k3x3_s1_w12_r152";
+    else pref = density < 0.2 ? "sconv_tile_wb_o4_y4_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o6_y4_x4_k3x3_s1_w12_r152";
+  } else if (k == 5 && g.kernel_w == 5) {
+    pref = "sconv_tile_wb_o4_y4_x4_k5x5_s1_w12_r152";
+  } else if (k == 1 && g.kernel_w == 1) {
+    pref = "sconv_tile_wb_o8_y2_x4_k1x1_s1_w16_r104";
+  }
+  if (const char *e = getenv("ESCORT_BWDW_VARIANT")) pref = e;
+  return pref ? find_variant(pref) + 1 : 0;
+}
+
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
-typedef CUresult (*TmaEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static TmaEncodeFn tma_encoder() {
   static TmaEncodeFn fn = nullptr;
   static bool tried = false;
@@ -186,6 +217,8 @@ std::vector<Slot> enumerate_slots(int GP, int BR, int PX, int order) {
 }
 }  // namespace
 
+static thread_local bool g_building_w = false;
+
 int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int layout_rank = plan->layout_rank;
   plan->tile = nullptr;
@@ -199,9 +232,11 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     vidx = variant - 1;
     if (vidx >= kNumVariants) return 0;
     const VariantDesc &v = kVariants[vidx];
-    if (!tile_variant_applies(plan, variant)) return 0;
+    if (v.MODE < 5 && !tile_variant_applies(plan, variant)) return 0;
+    // W (backward-weight) variants are built by tile_bwdw_build only, never as a forward kernel
+    if (v.MODE >= 5 && !(g_building_w && v.KH == g.kernel_h && v.KW == g.kernel_w && g.stride_h == 1 && g.stride_w == 1)) return 0;
   } else {
-    vidx = choose_variant(g, density);
+    vidx = choose_variant(g, density, out_dim(g.height, g.pad_h, g.kernel_h, g.stride_h, g.dilation_h));
     if (vidx < 0) return 0;
   }
   const VariantDesc &V = kVariants[vidx];
@@ -218,13 +253,13 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   // (sieve / rows variants are compiled for one patch-load plan: MODE 1, 3 = aligned body, MODE 2, 4 = patch aligned)
   const bool tma_ok = PAIR == 1 && g.width % 4 == 0 && g.pad_w == (KW - 1) / 2 && tma_encoder() != nullptr &&
                       !getenv("ESCORT_NO_TMA");
-  const bool plan_b_variant = V.MODE == 2 || V.MODE == 4;
+  const bool plan_b_variant = V.MODE == 2 || V.MODE == 4 || V.MODE == 6;
   // patch-aligned rows cannot come from TMA: a box starting at x = -pad_w faults (illegal instruction, measured on
   // B200) -- the innermost start coordinate must keep the global address 16-byte aligned, hence the aligned-body
   // layout for TMA and the cp.async loader for patch-aligned rows
   const bool use_tma_b = false;
   const bool use_tma = (tma_ok && !plan_b_variant) || use_tma_b;
-  if ((V.MODE == 1 || V.MODE == 3) && !use_tma) return 0;
+  if ((V.MODE == 1 || V.MODE == 3 || V.MODE == 5) && !use_tma) return 0;
   // aligned body (PAIR 1, TMA): data column 0 sits on a 16-byte boundary, HL = 4 halo columns to its left and the
   // lane base is the tile's first output column; patch aligned: the halo is exactly pad_w positions wide and the lane
   // base is the patch's first column
@@ -310,7 +345,8 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int per_slot = BR * PX;
   const int nslots = GP * per_slot;
   const int plane_f = R * P * PAIR;
-  const int hdr_bytes = ceil_div(WO * 4, 16) * 16;
+  // region header: WO segment offsets (+ WO tap bases for the backward-weight variants)
+  const int hdr_bytes = ceil_div((V.MODE >= 5 ? 2 : 1) * WO * 4, 16) * 16;
 
   // ---- nnz-balanced channel blocks: rows sorted by nnz (desc), dealt in snake order ----
   const std::vector<Nz> &nz = *plan->host_nz;
@@ -342,8 +378,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   CI = std::max(1, std::min(CI, 32));
   std::vector<uint4> prog;
   std::vector<int2> rtab;
-  std::vector<int> prog_pos;
-  int nchunks = 0, NS = 0, in_bytes = 0, stage_bytes = 0, max_region16 = 0, slot_f = 0;
+  std::vector<int> prog_pos, tapidx;
+  int nchunks = 0, NS = 0, in_bytes = 0, stage_bytes = 0, max_region16 = 0, slot_f = 0, max_seg_taps = 0, scratch_bytes = 0;
+  if (V.MODE >= 5) CI = std::max(1, std::min(CI, 6));  // short chunks keep the per-warp scratch rows small
   for (int attempt = 0; attempt < 8; ++attempt) {
     nchunks = ceil_div(Cg, CI);
     CI = ceil_div(Cg, nchunks);  // even out the chunks
@@ -361,7 +398,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     std::vector<unsigned> words;  // u32 stream, regions padded to 16 bytes
     rtab.assign((size_t)g.group * ogroups * nchunks, make_int2(0, 0));
     prog_pos.assign(nz.size(), -1);
+    tapidx.clear();
     max_region16 = 0;
+    max_seg_taps = 0;
     for (int gi = 0; gi < g.group; ++gi)
       for (int og = 0; og < ogroups; ++og)
         for (int c = 0; c < nchunks; ++c) {
@@ -370,7 +409,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
           for (int ow = 0; ow < WO; ++ow) {
             const int blk = og * WO + ow;
             words[region_start + ow] = (unsigned)((words.size() - region_start) * 4);  // byte offset of the segment
-            if (V.MODE >= 3) {
+            if (V.MODE == 3 || V.MODE == 4) {
               // rows stream (16-byte quads): H_0 | H_1 R_0.. | H_2 R_1.. | ... | H_END R_(n-1).. | slack quad; H = {plane
               // byte offset (END = ~0), mask words, pad}; R = the KW weights of one nonempty kernel row (absent taps 0),
               // rows of a step in (oc_local, kh) order.  Bit layout as in the sieve stream.
@@ -461,14 +500,19 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
                   for (int k = 0; k < NW; ++k) words.push_back(0u);
                 }
               };
+              if (V.MODE >= 5) words[region_start + WO + ow] = (unsigned)tapidx.size();
+              int seg_taps = 0;
               emit_hdr(0);
               for (size_t i = 0; i < steps.size(); ++i) {
                 emit_hdr(i + 1);
                 for (auto &wv : steps[i].w) {
                   prog_pos[wv.second] = (int)words.size();
                   words.push_back(wv.first);
+                  if (V.MODE >= 5) tapidx.push_back(wv.second);
+                  ++seg_taps;
                 }
               }
+              max_seg_taps = std::max(max_seg_taps, seg_taps);
               words.push_back(0u);  // the weight prefetch reads two words past the last weight
               words.push_back(0u);
               continue;
@@ -521,7 +565,8 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
         }
     const int prog_bytes = ceil_div(max_region16 * 16, 128) * 128;
     stage_bytes = ceil_div(in_bytes, 128) * 128 + prog_bytes;
-    NS = (int)std::min<long>((smem_budget - tab_bytes) / stage_bytes, 4L);
+    scratch_bytes = V.MODE >= 5 ? NCW * std::max(max_seg_taps, 1) * 128 : 0;
+    NS = (int)std::min<long>(std::max<long>(smem_budget - tab_bytes - scratch_bytes, 0L) / stage_bytes, 4L);
     if (NS >= 3 || (NS >= 2 && CI == 1)) {
       prog.resize(words.size() / 4);
       memcpy(prog.data(), words.data(), words.size() * 4);
@@ -553,7 +598,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     pr.lpr_shift = sh;
     pr.RO = 32 / lpr;
   }
-  tp->smem_bytes = (size_t)pr.stage0_off + (size_t)NS * stage_bytes;
+  pr.scratch_off = pr.stage0_off + NS * stage_bytes;
+  pr.scratch_rows = std::max(max_seg_taps, 1);
+  tp->smem_bytes = (size_t)pr.stage0_off + (size_t)NS * stage_bytes + (size_t)scratch_bytes;
   tp->nrecords = prog.size() * 2;
 
   // ---- lane table ----
@@ -569,7 +616,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   int rc = 0;
   if ((rc = upload_vec(&tp->d_lanes, lanes, stream)) || (rc = upload_vec(&tp->d_oc_list, oc_list, stream)) ||
       (rc = upload_vec(&tp->d_prog, prog, stream)) || (rc = upload_vec(&tp->d_rtab, rtab, stream)) ||
-      (rc = upload_vec(&tp->d_prog_pos, prog_pos, stream))) {
+      (rc = upload_vec(&tp->d_prog_pos, prog_pos, stream)) || (rc = upload_vec(&tp->d_tapidx, tapidx, stream))) {
     tile_plan_free(tp);
     return rc;
   }
@@ -579,6 +626,14 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     return cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
   }
   pr.lanes = tp->d_lanes; pr.oc_list = tp->d_oc_list; pr.prog = tp->d_prog; pr.rtab = tp->d_rtab;
+  pr.tapidx = tp->d_tapidx;
+  if (V.MODE >= 5) {
+    e = cudaFuncSetAttribute(V.bwdw, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+    if (e != cudaSuccess) {
+      tile_plan_free(tp);
+      return cuda_fail(e, "cudaFuncSetAttribute(smem)", __FILE__, __LINE__);
+    }
+  }
   // the attribute belongs to the kernel, not the plan: several plans share a variant, so always raise it to the
   // device's opt-in maximum instead of this plan's own size
   e = cudaFuncSetAttribute(V.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
@@ -624,6 +679,70 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
                   (void *)&nunits, (void *)&tmap};
   ESCORT_CUDA(cudaLaunchKernel(V.kernel, dim3(grid), dim3(V.NTW * 32), args, tp->smem_bytes, stream));
   return 0;
+}
+
+__global__ void zero_at_kernel(long nnz, const int *__restrict__ idx, float *__restrict__ dst) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) dst[idx[j]] = 0.f;
+}
+
+// Backward weight through a W variant's plan (plan->tile_w): gradients of the nonzero positions only, accumulated
+// into the dense weight_diff (always +=) and / or the CSR-ordered buffer (+= or overwritten).
+int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_diff, float *wd_dense, float *wd_csr,
+              int accumulate, cudaStream_t stream) {
+  TilePlan *tp = plan->tile_w;
+  TileParams prm = tp->prm;
+  prm.n_igroups = ceil_div(num, prm.G);
+  prm.dense_idx = plan->d_dense_idx;
+  prm.csr_pos = plan->d_csr_pos;
+  int nunits = (int)((size_t)prm.n_igroups * prm.nbands * prm.ngroups * prm.ogroups);
+  const unsigned grid = (unsigned)std::min(nunits, tp->num_sms);
+  const VariantDesc &V = kVariants[tp->vidx];
+  if (!accumulate && wd_csr) {  // the dense diff always accumulates (Caffe's contract); the CSR-ordered copy may be overwritten
+    const unsigned blocks = (unsigned)((plan->nnz + 255) / 256);
+    zero_at_kernel<<<blocks, 256, 0, stream>>>(plan->nnz, plan->d_csr_pos, wd_csr);
+    ESCORT_LAUNCH_CHECK();
+  }
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (prm.use_tma) {
+    if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) {
+      set_last_error("escort_sconv_backward_weight: bottom must be 16-byte aligned for the TMA-staged kernel");
+      return ESCORT_EINVAL;
+    }
+    const cuuint64_t dims[4] = {(cuuint64_t)prm.W, (cuuint64_t)prm.H, (cuuint64_t)prm.C, (cuuint64_t)num};
+    const cuuint64_t strides[3] = {(cuuint64_t)prm.W * 4, (cuuint64_t)prm.H * prm.W * 4,
+                                   (cuuint64_t)prm.C * prm.H * prm.W * 4};
+    const cuuint32_t box[4] = {(cuuint32_t)prm.P, (cuuint32_t)prm.R, (cuuint32_t)prm.CI, 1u};
+    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+    CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(bottom), dims, strides, box,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_last_error("escort_sconv_backward_weight: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+      return ESCORT_EINVAL;
+    }
+  }
+  void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&top_diff, (void *)&wd_dense, (void *)&wd_csr,
+                  (void *)&nunits, (void *)&tmap};
+  ESCORT_CUDA(cudaLaunchKernel(V.bwdw, dim3(grid), dim3(V.NTW * 32), args, tp->smem_bytes, stream));
+  return 0;
+}
+
+// build plan->tile_w (the backward-weight plan) with the default W variant; leaves it null if none applies
+int tile_bwdw_build(escort_plan *plan, cudaStream_t stream) {
+  const int v = tile_bwdw_variant(plan);
+  if (v <= 0) return 0;
+  TilePlan *fwd = plan->tile;
+  const int rank = plan->layout_rank;
+  plan->layout_rank = 0;
+  g_building_w = true;
+  int rc = tile_plan_build(plan, v, stream);
+  g_building_w = false;
+  plan->tile_w = plan->tile;
+  plan->tile = fwd;
+  plan->layout_rank = rank;
+  return rc;
 }
 
 __global__ void tile_refresh_kernel(long nnz, const float *__restrict__ w_dense, const int *__restrict__ dense_idx,

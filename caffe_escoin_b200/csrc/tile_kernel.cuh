@@ -39,6 +39,12 @@ struct TileParams {
   const uint4 *prog;       // program regions (16-byte units)
   const int2 *rtab;        // [ngroups*ogroups*nchunks] {offset, length} of a region in 16-byte units
   int lpr_shift, RO;       // loader: log2(lanes per row), rows per warp-wide copy instruction
+  // backward weight ("W" variants): per-warp scratch rows P[tap ordinal][lane] behind the stage ring
+  int scratch_off;         // byte offset of the scratch area in dynamic smem
+  int scratch_rows;        // rows (taps) per warp = the longest segment of the plan
+  const int *tapidx;       // stream-order tap -> row-major nonzero index
+  const int *dense_idx;    // nonzero -> index in the dense weight tensor   (filled per launch)
+  const int *csr_pos;      // nonzero -> position in the reference's CSR blob layout
 };
 
 #ifndef ESCORT_TILE_DEVICE_ONLY
@@ -53,6 +59,7 @@ struct TilePlan {
   uint4 *d_prog;
   int2 *d_rtab;
   int *d_prog_pos;         // [nnz] row-major nonzero -> 4-byte word index of its weight in d_prog
+  int *d_tapidx;           // W variants: stream-order tap -> row-major nonzero index
   size_t nrecords;
   int num_sms;
 };
@@ -148,41 +155,16 @@ __device__ __forceinline__ void load_chunk(const TileParams &p, const float *__r
   }
 }
 
+// loader warps: stream input chunks + byte-code regions through the stage ring (shared by the forward and the
+// backward-weight kernel)
 template <int VID>
-__global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
-    sconv_tile_kernel(const TileParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias,
-                      int fuse_relu, float *__restrict__ top, int nunits, const __grid_constant__ CUtensorMap tmap) {
+__device__ __forceinline__ void tile_loader_loop(const TileParams &p, int num, const float *__restrict__ bottom, int nunits,
+                                                 const CUtensorMap &tmap, unsigned char *smem_raw, unsigned smem_base, int wid,
+                                                 int lane) {
   using IP = Interp<VID>;
-  constexpr int OT = IP::OT, TY = IP::TY, TX = IP::TX, S = IP::S, PAIR = IP::PAIR;
-  constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = IP::NTW * 32;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
-  // the broadcast tells ptxas that wid is warp-uniform: everything derived from it (the byte-code segment address,
-  // hence every header word loaded from it) is then uniform too, and the skip branches of the sieve / rows variants
-  // compile to plain branches without per-step SHFL + R2UR or BSSY/BSYNC reconvergence bookkeeping
-  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  constexpr int TY = IP::TY, S = IP::S, PAIR = IP::PAIR;
+  constexpr int NCW = IP::NCW, NLW = IP::NLW;
   const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
-
-  // one-time set-up: barriers, zero halo (all stages), loader scatter table
-  if (tid == 0) {
-    for (int s = 0; s < p.NS; ++s) {
-      mbar_init(full_bar + 8 * s, NLW * 32);
-      mbar_init(empty_bar + 8 * s, NCW);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  {
-    float4 *st4 = reinterpret_cast<float4 *>(smem_raw + p.stage0_off);
-    const int n4 = (p.NS * p.stage_bytes) >> 4;
-    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int i = tid; i < n4; i += NT) st4[i] = z;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the TMA path overwrites these bytes
-  }
-  __syncthreads();
-
-  if (wid >= NCW) {
-    // ================= loader warps: stream input chunks + byte-code regions through the stage ring ==========
     if constexpr (IP::CREGS > 0) {
       // the loader warpgroup hands its registers to the compute warpgroups; its idle warps leave
       asm volatile("setmaxnreg.dec.sync.aligned.u32 40;" ::: "memory");
@@ -233,6 +215,44 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar + 8 * s) : "memory");
       }
     }
+}
+
+template <int VID>
+__global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
+    sconv_tile_kernel(const TileParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias,
+                      int fuse_relu, float *__restrict__ top, int nunits, const __grid_constant__ CUtensorMap tmap) {
+  using IP = Interp<VID>;
+  constexpr int OT = IP::OT, TY = IP::TY, TX = IP::TX, S = IP::S, PAIR = IP::PAIR;
+  constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = IP::NTW * 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the broadcast tells ptxas that wid is warp-uniform: everything derived from it (the byte-code segment address,
+  // hence every header word loaded from it) is then uniform too, and the skip branches of the sieve / rows variants
+  // compile to plain branches without per-step SHFL + R2UR or BSSY/BSYNC reconvergence bookkeeping
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
+
+  // one-time set-up: barriers, zero halo (all stages), loader scatter table
+  if (tid == 0) {
+    for (int s = 0; s < p.NS; ++s) {
+      mbar_init(full_bar + 8 * s, NLW * 32);
+      mbar_init(empty_bar + 8 * s, NCW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  {
+    float4 *st4 = reinterpret_cast<float4 *>(smem_raw + p.stage0_off);
+    const int n4 = (p.NS * p.stage_bytes) >> 4;
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < n4; i += NT) st4[i] = z;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the TMA path overwrites these bytes
+  }
+  __syncthreads();
+
+  if (wid >= NCW) {
+    // ================= loader warps: stream input chunks + byte-code regions through the stage ring ==========
+    tile_loader_loop<VID>(p, num, bottom, nunits, tmap, smem_raw, smem_base, wid, lane);
     return;
   }
 
@@ -306,6 +326,106 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
   }
 }
 
+// ---- backward weight: same units, same loader, same stage ring as the forward kernel.  A compute lane keeps its
+// OT x TY x TX tile of top_diff in registers for the whole unit; per staged chunk the W variant's handler chain leaves
+// one partial per executed tap and lane in the warp's scratch rows, the warp sums every row over its lanes and adds
+// it to the weight gradient (dense layout and / or the reference's CSR blob layout) with one atomic per tap.
+template <int VID>
+__global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
+    sconv_tile_bwdw_kernel(const TileParams p, int num, const float *__restrict__ bottom, const float *__restrict__ top_diff,
+                           float *__restrict__ wd_dense, float *__restrict__ wd_csr, int nunits,
+                           const __grid_constant__ CUtensorMap tmap) {
+  using IP = Interp<VID>;
+  if constexpr (IP::MODE >= 5) {
+    constexpr int OT = IP::OT, TY = IP::TY, TX = IP::TX;
+    constexpr int NCW = IP::NCW, NLW = IP::NLW, NT = IP::NTW * 32;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const unsigned full_bar = smem_base, empty_bar = smem_base + 8 * kMaxStages;
+    if (tid == 0) {
+      for (int s = 0; s < p.NS; ++s) {
+        mbar_init(full_bar + 8 * s, NLW * 32);
+        mbar_init(empty_bar + 8 * s, NCW);
+      }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+      float4 *st4 = reinterpret_cast<float4 *>(smem_raw + p.stage0_off);
+      const int n4 = (p.NS * p.stage_bytes) >> 4;
+      const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = tid; i < n4; i += NT) st4[i] = z;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+    if (wid >= NCW) {
+      tile_loader_loop<VID>(p, num, bottom, nunits, tmap, smem_raw, smem_base, wid, lane);
+      return;
+    }
+    if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
+    const unsigned lane_base_off = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+    const unsigned pitch_bytes = (unsigned)p.P * 4u;
+    float *scratch = reinterpret_cast<float *>(smem_raw + p.scratch_off) + (size_t)wid * p.scratch_rows * 32;
+    const unsigned scratch_lane = smem_base + p.scratch_off + ((unsigned)wid * p.scratch_rows * 32 + lane) * 4u;
+    float dy[IP::NACC];
+    unsigned s = 0, ph = 0;
+    const int pw = wid % p.WP, ow = wid / p.WP;
+    const unsigned ow4 = 4u * (unsigned)ow;
+#pragma unroll 1
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+      {  // the lane's tile of top_diff (zero outside the image / the batch / the layer)
+        const UnitCoord uc = decode_unit(p, u);
+        const int blk = uc.og * p.WO + ow;
+        const int slot = pw * 32 + lane;
+        const bool lane_ok = blk < p.nblk && slot < p.nslots;
+        const int4 li = p.lanes[slot < p.WP * 32 ? slot : 0];
+        const int n = uc.n0 + li.y;
+        const int y0 = (uc.band * p.BR + li.z) * TY, x0 = li.w * TX;
+#pragma unroll
+        for (int o = 0; o < OT; ++o) {
+          const int oc = lane_ok ? p.oc_list[((size_t)uc.cg * p.nblk + blk) * OT + o] : -1;
+          const float *src = top_diff + (((size_t)n * p.M + (oc < 0 ? 0 : oc)) * p.Ho) * p.Wo;
+#pragma unroll
+          for (int ty = 0; ty < TY; ++ty)
+#pragma unroll
+            for (int tx = 0; tx < TX; ++tx) {
+              const int y = y0 + ty, x = x0 + tx;
+              const bool ok = oc >= 0 && n < num && y < p.Ho && x < p.Wo;
+              dy[(o * TY + ty) * TX + tx] = ok ? __ldg(src + (size_t)y * p.Wo + x) : 0.f;
+            }
+        }
+      }
+#pragma unroll 1
+      for (int c = 0; c < p.nchunks; ++c) {
+        mbar_wait(full_bar + 8 * s, ph);
+        const unsigned stage = smem_base + p.stage0_off + s * p.stage_bytes;
+        const unsigned region = stage + p.in_bytes;
+        unsigned seg, tapbase;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(seg) : "r"(region + ow4));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tapbase) : "r"(region + 4u * (unsigned)p.WO + ow4));
+        const unsigned ntaps = IP::run_w(dy, region + seg, stage + lane_base_off, pitch_bytes, scratch_lane);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty_bar + 8 * s);  // the stage is no longer read: the sums live in the scratch rows
+        for (unsigned k = lane; k < ntaps; k += 32) {
+          const float *row = scratch + (size_t)k * 32;
+          float sum = 0.f;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) sum += row[(l + lane) & 31];  // rotated: one bank per lane
+          const int j = __ldg(p.tapidx + tapbase + k);
+          if (wd_dense) atomicAdd(wd_dense + __ldg(p.dense_idx + j), sum);
+          if (wd_csr) atomicAdd(wd_csr + __ldg(p.csr_pos + j), sum);
+        }
+        __syncwarp();
+        if (++s == (unsigned)p.NS) {
+          s = 0;
+          ph ^= 1u;
+        }
+      }
+    }
+  }
+}
+
 // ---- interpreter-only microbenchmark: no loader, no barriers.  Every active warp walks the same synthetic
 // byte-code (already in the interpreter's record format) `iters` times against a zeroed input area; measures the
 // dispatch + FMA ceiling of a variant in isolation (tools/interp_bench.py).
@@ -330,7 +450,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
 #pragma unroll
   for (int i = 0; i < IP::NACC; ++i) acc[i] = 0.f;
 #pragma unroll 1
-  for (int it = 0; it < iters; ++it) IP::run(acc, smem_base + kIn, smem_base + (tid & 31) * 16u, 128u * IP::PAIR, 0u);
+  for (int it = 0; it < (IP::MODE >= 5 ? 0 : iters); ++it) IP::run(acc, smem_base + kIn, smem_base + (tid & 31) * 16u, 128u * IP::PAIR, 0u);
   float sum = 0.f;
 #pragma unroll
   for (int i = 0; i < IP::NACC; ++i) sum += acc[i];

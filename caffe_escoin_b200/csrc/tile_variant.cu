@@ -12,6 +12,9 @@ namespace escort {
 const void *ESCORT_CAT(tile_variant_kernel_, ESCORT_VARIANT_ID)() {
   return (const void *)&sconv_tile_kernel<ESCORT_VARIANT_ID>;
 }
+const void *ESCORT_CAT(tile_variant_bwdw_, ESCORT_VARIANT_ID)() {
+  return (const void *)&sconv_tile_bwdw_kernel<ESCORT_VARIANT_ID>;
+}
 const void *ESCORT_CAT(tile_variant_bench_, ESCORT_VARIANT_ID)() {
   return (const void *)&interp_bench_kernel<ESCORT_VARIANT_ID>;
 }

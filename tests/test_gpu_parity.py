@@ -274,12 +274,19 @@ BWD_CASES = [
     (2, 12, 12, 14, 14, 3, 3, 2, 1, 1, 1, 0.50),
     (1, 6, 10, 11, 9, 3, 3, 1, 2, 2, 1, 0.60),
     (2, 16, 8, 7, 7, 1, 1, 1, 0, 1, 1, 0.50),
+    (2, 4, 6, 12, 12, 5, 5, 1, 0, 1, 1, 0.80),      # LeNet-like: no padding -> backward data pads by k-1
+    (5, 32, 32, 56, 56, 3, 3, 1, 1, 1, 1, 0.70),    # odd batch, TMA-staged backward data
 ]
 
 
+@pytest.mark.parametrize("generic_bwd", [False, True], ids=["tile", "generic"])
 @pytest.mark.parametrize("case", BWD_CASES, ids=lambda c: "N%d_C%d_M%d_H%dx%d_k%dx%d_s%d_p%d_d%d_g%d_sp%g" % c)
-def test_backward_vs_oracle(capi, po, case):
+def test_backward_vs_oracle(capi, po, case, generic_bwd, monkeypatch):
     torch = _torch()
+    if generic_bwd:
+        monkeypatch.setenv("ESCORT_GENERIC_BACKWARD", "1")   # the one-thread-per-element kernels (any stride / dilation)
+    else:
+        monkeypatch.delenv("ESCORT_GENERIC_BACKWARD", raising=False)
     from caffe_escoin_b200 import workloads as wl
     N, Cin, Cout, H, W, kh, kw, s, p, dil, grp, sp = case
     rng = np.random.default_rng(hash(case) % (2 ** 31))

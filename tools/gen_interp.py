@@ -26,44 +26,10 @@ OUTDIR = os.path.join(ROOT, "caffe_escoin_b200", "csrc", "generated")
 # (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW): channel block, tile, kernel taps, stride, images per lane,
 # compute warps, loader warps.  8 warps/CTA (2 per SM sub-partition) allow 255 registers; 12 allow 168.
 VARIANTS = [
-    # 3x3 stride 1
-    (8, 2, 4, 3, 3, 1, 1, 16, 4),
-    (4, 2, 4, 3, 3, 1, 1, 20, 4),
-    (4, 4, 4, 3, 3, 1, 1, 14, 2),
-    (8, 4, 4, 3, 3, 1, 1, 6, 2),
-    (2, 4, 4, 3, 3, 1, 1, 16, 4),
-    (4, 2, 4, 3, 3, 1, 2, 14, 2),
-    (4, 4, 4, 3, 3, 1, 2, 6, 2),
-    (8, 2, 4, 3, 3, 1, 2, 6, 2),
-    # 5x5 stride 1
-    (4, 2, 4, 5, 5, 1, 1, 14, 2),
-    (4, 4, 4, 5, 5, 1, 1, 6, 2),
-    (4, 2, 4, 5, 5, 1, 2, 6, 2),
-    # 1x1
-    (8, 2, 4, 1, 1, 1, 1, 16, 4),
-    (8, 2, 4, 1, 1, 1, 2, 6, 2),
-    # 3x3 stride 2
-    (8, 2, 4, 3, 3, 2, 1, 14, 2),
-    (4, 2, 4, 3, 3, 2, 2, 6, 2),
-    # ---- second generation: more FMAs per dispatched record at >= 2 warps per scheduler.  The register file is
-    # split per scheduler (16K registers each): 8 / 12 / 16 warps per CTA allow 255 / 168 / 128 registers; a trailing
-    # CREGS re-balances registers between the loader warpgroup and the compute warpgroups (setmaxnreg) ----
-    (6, 4, 4, 3, 3, 1, 1, 10, 2),        # 16
-    (7, 4, 4, 3, 3, 1, 1, 10, 2),
-    (3, 7, 4, 3, 3, 1, 1, 10, 2),
-    (6, 7, 4, 3, 3, 1, 1, 6, 2),
-    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232),    # 20
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232),
-    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152),
+    # the first-generation indirect-branch interpreter, kept for comparison (winners of the first B200 sweep)
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152),
     (4, 4, 4, 3, 3, 1, 2, 8, 4, 232),
     (4, 4, 4, 5, 5, 1, 1, 10, 2),
-    (5, 4, 4, 5, 5, 1, 1, 10, 2),        # 25
-    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232),
-    (6, 4, 4, 5, 5, 1, 1, 8, 4, 232),
-    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152),   # 28
-    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152),
-    (2, 7, 4, 3, 3, 1, 1, 14, 2),
-    (2, 7, 4, 5, 5, 1, 1, 12, 4, 152),
 ]
 
 
@@ -73,42 +39,36 @@ VARIANTS = [
 # (whole channel / whole kernel row first, then single taps).  Weights are a plain fp32 stream consumed in order.
 # Same tuple layout as VARIANTS.
 SIEVE = [
-    # 3x3 stride 1 (1-based variant ids start at 32).  Trailing letter = patch-load plan the variant is compiled for:
-    # "a" aligned body (rows staged by TMA), "b" patch aligned (rows staged by the cp.async loader)
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),    # 32
+    # Trailing letter = patch-load plan the variant is compiled for: "a" aligned body (rows staged by TMA),
+    # "b" patch aligned (rows staged by the cp.async loader)
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
-    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),
-    (5, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),    # 35
-    (6, 7, 4, 3, 3, 1, 1, 6, 2, 0, "a"),
-    (6, 7, 4, 3, 3, 1, 1, 6, 2, 0, "b"),
-    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
-    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 39
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
-    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 42
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
+    (2, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     (8, 4, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
-    (10, 4, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
-    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),   # 45
-    (8, 2, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     # 5x5 stride 1
-    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "a"),    # 47
+    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "a"),
     (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "b"),
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
-    (6, 4, 4, 5, 5, 1, 1, 8, 4, 232, "b"),    # 50
+    (6, 4, 4, 5, 5, 1, 1, 8, 4, 232, "b"),
     # 1x1
     (8, 2, 4, 1, 1, 1, 1, 16, 4, 104, "b"),
     (6, 7, 4, 1, 1, 1, 1, 8, 4, 232, "b"),
     # 3x3 stride 2
-    (4, 4, 4, 3, 3, 2, 1, 8, 4, 232, "b"),    # 53
+    (4, 4, 4, 3, 3, 2, 1, 8, 4, 232, "b"),
     (8, 2, 4, 3, 3, 2, 1, 12, 4, 152, "b"),
 ]
 # rolling-row-predicate editions (appended after ROWS so earlier ids stay put)
 SIEVE_R = [
-    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a", 1),   # 75
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a", 1),
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", 1),
-    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 79
+    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
 ]
@@ -308,6 +268,165 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
     return "\n".join(src)
 
 
+# ---- backward weight through the same machinery ("W" variants).  The lane keeps its OT x TY x TX tile of TOP DIFF in
+# registers (read-only operands) and walks the forward sieve stream of the block: for every nonzero tap it forms
+# sum_t dy[o][t] * x[t + (kh, kw)] over its tile (four independent FMA chains) and stores the partial to the warp's
+# scratch row P[tap ordinal][lane] in shared memory.  The caller then sums each row over the lanes and adds it to the
+# weight gradient (one atomic per tap, unit and chunk).  Weights in the stream are skipped (pc advances by popcount).
+# tuple: (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN)
+BWDW = [
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
+    (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
+    (8, 2, 4, 1, 1, 1, 1, 16, 4, 104, "b"),
+]
+
+
+def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
+    assert PAIR == 1
+    NACC = OT * TY * TX
+    PR = (TY - 1) * S + KH
+    PC = (TX - 1) * S + KW
+    loads, loads_a, XW, PADL = load_plans(PC, PAIR, KW)
+    NX = PR * XW
+    NC = OT * KH * KW
+    NR = OT * KH
+    OPW, NW = sieve_layout(OT, KH, KW)
+    HB = 4 * (1 + NW)
+    NOPS = NACC
+    L = []
+    a = L.append
+    a("{")
+    a(".reg .f32 x<%d>, s<4>;" % NX)
+    a(".reg .b32 pc, pp, off, noff, t, t2, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
+    a(".reg .pred p, pr<3>, pt<%d>;" % KW)
+    # operands: %0 = taps executed (out), %1.. = dy tile, then prog, lane_base, pitch_bytes, scratch (lane's column)
+    I0 = 1
+    a("mov.u32 pc, %%%d;" % (I0 + NOPS))
+    a("mov.u32 pp, %%%d;" % (I0 + NOPS + 3))
+    a("ld.shared.b32 off, [pc];")
+    for k in range(NW):
+        a("ld.shared.b32 m%d, [pc+%d];" % (k, 4 + 4 * k))
+    a("shfl.sync.idx.b32 off, off, 0, 0x1f, 0xffffffff;")
+    for k in range(NW):
+        a("shfl.sync.idx.b32 m%d, m%d, 0, 0x1f, 0xffffffff;" % (k, k))
+    a("add.u32 pc, pc, %d;" % HB)
+    a("WLOOP:")
+    a("setp.eq.u32 p, off, 0xffffffff;")
+    a("@p bra.uni WDONE;")
+    a("ld.shared.b32 noff, [pc];")
+    for k in range(NW):
+        a("ld.shared.b32 nm%d, [pc+%d];" % (k, 4 + 4 * k))
+    a("popc.b32 t, m0;")
+    for k in range(1, NW):
+        a("popc.b32 t2, m%d;" % k)
+        a("add.u32 t, t, t2;")
+    a("shl.b32 t, t, 2;")
+    a("add.u32 pc, pc, t;")
+    a("add.u32 pc, pc, %d;" % HB)
+    a("shfl.sync.idx.b32 noff, noff, 0, 0x1f, 0xffffffff;")
+    for k in range(NW):
+        a("shfl.sync.idx.b32 nm%d, nm%d, 0, 0x1f, 0xffffffff;" % (k, k))
+
+    def rowmask(r):
+        o, kh = r // KH, r % KH
+        return o // OPW, ((1 << KW) - 1) << ((o % OPW) * KH * KW + kh * KW)
+
+    def set_row_pred(r):
+        wd, msk = rowmask(r)
+        a("and.b32 t, m%d, 0x%x;" % (wd, msk))
+        a("setp.ne.u32 pr%d, t, 0;" % (r % 3))
+    set_row_pred(0)
+    if NR > 1:
+        set_row_pred(1)
+    a("add.u32 ad0, %%%d, off;" % (I0 + NOPS + 1))
+    for r in range(1, PR):
+        a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, I0 + NOPS + 2))
+    plan = loads_a if PLAN == "a" else loads
+    for r in range(PR):
+        for (po, cnt, byte) in plan:
+            b = r * XW + po
+            sgn = "+%d" % byte
+            if cnt == 4:
+                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+            elif cnt == 2:
+                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+            else:
+                a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+    for r in range(NR):
+        o, kh = r // KH, r % KH
+        wd, ob = o // OPW, (o % OPW) * KH * KW
+        a("WRR%d:" % r)
+        if r + 2 < NR:
+            set_row_pred(r + 2)
+        a("@!pr%d bra.uni WRR%d;" % (r % 3, r + 1))
+        if KW > 1:
+            for kw in range(KW):
+                a("and.b32 t, m%d, 0x%x;" % (wd, 1 << (ob + kh * KW + kw)))
+                a("setp.ne.u32 pt%d, t, 0;" % kw)
+        for kw in range(KW):
+            c = (o * KH + kh) * KW + kw
+            if KW > 1:
+                a("@!pt%d bra.uni WH%dE;" % (kw, c))
+            n = 0
+            for ty in range(TY):
+                for tx in range(TX):
+                    acc = (o * TY + ty) * TX + tx
+                    xi = (ty * S + kh) * XW + tx * S + kw
+                    if n < 4:
+                        a("mul.rn.f32 s%d, %%%d, x%d;" % (n, I0 + acc, xi))
+                    else:
+                        a("fma.rn.f32 s%d, %%%d, x%d, s%d;" % (n % 4, I0 + acc, xi, n % 4))
+                    n += 1
+            a("add.rn.f32 s0, s0, s1;")
+            a("add.rn.f32 s2, s2, s3;")
+            a("add.rn.f32 s0, s0, s2;")
+            a("st.shared.f32 [pp], s0;")
+            a("add.u32 pp, pp, 128;")
+            a("WH%dE:" % c)
+    a("WRR%d:" % NR)
+    a("mov.b32 off, noff;")
+    for k in range(NW):
+        a("mov.b32 m%d, nm%d;" % (k, k))
+    a("bra.uni WLOOP;")
+    a("WDONE:")
+    a("sub.u32 pp, pp, %%%d;" % (I0 + NOPS + 3))
+    a("shr.u32 %0, pp, 7;")
+    a("}")
+    body = "\n".join('      "%s\\n\\t"' % s for s in L)
+    ops_in = ", ".join('"f"(acc[%d])' % i for i in range(NOPS))
+    name = "w%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, OT, TY, TX, KH, KW, S, NCW, "_r%d" % CREGS if CREGS else "")
+    src = []
+    src.append("// ---- backward-weight variant %s: %d top-diff registers, %d patch registers, %d handlers ----"
+               % (name, NACC, NX, NC))
+    src.append("template <> struct Interp<%d> {" % vid)
+    src.append("  static constexpr int OT = %d, TY = %d, TX = %d, KH = %d, KW = %d, S = %d, PAIR = %d;"
+               % (OT, TY, TX, KH, KW, S, PAIR))
+    src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;" % (NOPS, NC, PR, PC, XW, PADL))
+    NTW = NCW + (4 if CREGS else NLW)
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;" % (NCW, NLW, NTW, CREGS, 5 if PLAN == "a" else 6))
+    src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
+    src.append("  // returns the number of taps executed (= scratch rows written)")
+    src.append("  __device__ __forceinline__ static unsigned run_w(const float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
+    src.append("                                                   unsigned pitch_bytes, unsigned scratch) {")
+    src.append("    unsigned ntaps;")
+    src.append("    asm volatile(")
+    src.append(body)
+    src.append('      : "=r"(ntaps)')
+    src.append("      : %s," % ops_in)
+    src.append('        "r"(prog), "r"(lane_base), "r"(pitch_bytes), "r"(scratch)')
+    src.append('      : "memory");')
+    src.append("    return ntaps;")
+    src.append("  }")
+    src.append("  __device__ __forceinline__ static void run(float (&)[%d], unsigned, unsigned, unsigned, unsigned) {}" % NOPS)
+    src.append("};")
+    return "\n".join(src)
+
+
 # ---- fourth generation ("rows"): the unit of control flow is a kernel ROW (oc_local, kh).  Empty rows are skipped
 # with a warp-uniform direct branch; inside a nonempty row the KW taps are straight-line code, each FMA guarded by
 # a predicate (absent taps issue but do not execute).  A taken branch costs ~50 cycles of front-end redirect, a
@@ -318,28 +437,7 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
 # tuple: (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN, TAP)  TAP: "p" predicated, "j" branch per tap, "d" dense
 ROWS = [
     # 3x3, two images per lane (FFMA2), patch-aligned rows
-    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),    # 56
     (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "j"),
-    (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "d"),
-    (2, 4, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),
-    (4, 2, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),   # 60
-    (5, 2, 4, 3, 3, 1, 2, 12, 4, 152, "b", "p"),
-    (8, 2, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),
-    (6, 2, 4, 3, 3, 1, 2, 8, 4, 232, "b", "p"),
-    # 3x3, one image per lane
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", "p"),    # 64
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", "p"),
-    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a", "p"),
-    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", "p"),
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", "d"),    # 68
-    (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", "p"),
-    # 5x5
-    (4, 2, 4, 5, 5, 1, 2, 8, 4, 232, "b", "p"),    # 70
-    (2, 4, 4, 5, 5, 1, 2, 8, 4, 232, "b", "p"),
-    (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", "p"),
-    (4, 7, 4, 5, 5, 1, 1, 8, 4, 232, "b", "p"),
-    # 3x3 stride 2
-    (4, 2, 4, 3, 3, 2, 2, 8, 4, 232, "b", "p"),    # 74
 ]
 
 
@@ -647,10 +745,11 @@ def main():
             "#pragma once",
             "template <int VID> struct Interp;"]
     ALL = ([(v, 0) for v in VARIANTS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE] +
-           [(v, 3 if v[10] == "a" else 4) for v in ROWS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE_R])
+           [(v, 3 if v[10] == "a" else 4) for v in ROWS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE_R] +
+           [(v, 5 if v[10] == "a" else 6) for v in BWDW])
     for i, (v, mode) in enumerate(ALL):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
-        txt = "\n".join(head + [(gen_variant, gen_sieve, gen_sieve, gen_rows, gen_rows)[mode](i, *v)]) + "\n"
+        txt = "\n".join(head + [(gen_variant, gen_sieve, gen_sieve, gen_rows, gen_rows, gen_bwdw, gen_bwdw)[mode](i, *v)]) + "\n"
         if not os.path.exists(path) or open(path).read() != txt:
             open(path, "w").write(txt)
     lst = os.path.join(OUTDIR, "variant_list.inc")
@@ -667,6 +766,6 @@ def main():
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "--count":
-        print(len(VARIANTS) + len(SIEVE) + len(ROWS) + len(SIEVE_R))
+        print(len(VARIANTS) + len(SIEVE) + len(ROWS) + len(SIEVE_R) + len(BWDW))
     else:
         main()

@@ -45,13 +45,15 @@ def _peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def _workload(name):
+def _workload(name, train=False):
     from caffe_escoin_b200 import workloads as wl
     specs = {"alexnet": wl.ALEXNET, "googlenet": wl.GOOGLENET, "resnet50": wl.RESNET50, "lenet": wl.LENET}[name]
     label = {"alexnet": "alexnet_conv2-conv5_pruned85-88_fwd_b256",
              "googlenet": "googlenet_v1_3x3_5x5_pruned75_fwd_b128",
              "resnet50": "resnet50_branch2b_3x3_pruned70_fwd_b256",
              "lenet": "lenet5_conv1-2_pruned80_fwd_b64"}[name]
+    if train:
+        label = label.replace("_fwd_", "_fwd+masked-bwd_")
     return specs, label
 
 
@@ -222,6 +224,8 @@ def run_ours(args, specs, label):
             plan.autotune(spec.N)
             tune_cache[spec.name] = list(plan.get_config())
             tune_dirty = True
+        if args.train and args.variant is None:
+            plan.autotune_backward(spec.N)
         x = torch.from_numpy(d["x"]).cuda()
         b = torch.from_numpy(d["bias"]).cuda() if d["bias"] is not None else None
         y = torch.empty((spec.N, spec.Cout, plan.Ho, plan.Wo), device="cuda")
@@ -229,26 +233,72 @@ def run_ours(args, specs, label):
         layers.append(dict(spec=spec, plan=plan, x=x, b=b, y=y, flops=flops, bytes=byts, csr=csr))
         host_in.append(torch.from_numpy(d["x"]).pin_memory())
         host_out.append(torch.empty(y.shape, dtype=torch.float32).pin_memory())
+        if args.train:
+            Lr = layers[-1]
+            g = torch.Generator(device="cuda").manual_seed(1701 + li)
+            Lr["dy"] = torch.rand(y.shape, device="cuda", generator=g) * 2 - 1
+            Lr["dx"] = torch.empty_like(x)
+            Lr["db"] = torch.zeros(spec.Cout, device="cuda") if b is not None else None
+            # CSR-ordered gradient in the reference's blob layout: group g at offset weight_offset * g
+            Mg, Cg = spec.Cout // spec.group, spec.Cin // spec.group
+            wo = Mg * Cg * spec.k * spec.k
+            rp = csr["rowptr"].cpu().numpy()
+            Lr["gsize"] = wo * (spec.group - 1) + int(rp[(Mg + 1) * spec.group - 1])
+            host_in.append(Lr["dy"].cpu().pin_memory())
+            host_out.append(torch.empty(x.shape, dtype=torch.float32).pin_memory())
     if args.tune_cache and tune_dirty and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.tune_cache)), exist_ok=True)
         json.dump(tune_cache, open(args.tune_cache, "w"))
     N = specs[0].N
     nl = len(layers)
 
+    # the step as a list of timed operations: (layer index, kind, callable); every operation is one launch of ours
+    flat = None
+    if args.train:
+        offs, tot = [], 0
+        for Lr in layers:
+            offs.append(tot)
+            tot += (Lr["gsize"] + 3) // 4 * 4
+        flat = torch.zeros(tot, device="cuda")   # the flat gradient buffer the exchange step reduces (parallel.cpp:75-108)
+        for Lr, o in zip(layers, offs):
+            Lr["wd"] = flat[o:o + Lr["gsize"]]
+    ops = []
+    for i, L in enumerate(layers):
+        if not args.train:
+            ops.append((i, "fwd", lambda L=L: L["plan"].forward(L["x"], L["b"], relu=True, top=L["y"])))
+        else:
+            ops.append((i, "fwd", lambda L=L: L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"])))
+            ops.append((i, "bwd_weight", lambda L=L: L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"],
+                                                                               accumulate=False)))
+            ops.append((i, "bwd_data", lambda L=L: L["plan"].backward_data(L["dy"], L["dx"])))
+    nops = len(ops)
+
+    def exchange():
+        # the path's one exchange step: sum over ranks, then 1/N (NCCL<Dtype>::on_gradients_ready, parallel.cpp:238-256)
+        if not args.train:
+            return
+        for L in layers:
+            if L["db"] is not None:
+                capi.bias_backward(L["dy"], L["db"])
+        if world > 1:
+            dist.all_reduce(flat)
+            capi.allreduce_grads(flat, 1.0 / world)
+
     def step(events=None):
-        for i, L in enumerate(layers):
+        for k, (i, kind, fn) in enumerate(ops):
             if events is not None:
-                events[i][0].record()
-            L["plan"].forward(L["x"], L["b"], relu=True, top=L["y"])
+                events[k][0].record()
+            fn()
             if events is not None:
-                events[i][1].record()
+                events[k][1].record()
+        exchange()
 
     # ---- value: inputs resident in HBM ----
     for _ in range(args.warmup):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nl)]
+    evs = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nops)]
            for _ in range(args.steps)]
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -265,7 +315,7 @@ def run_ours(args, specs, label):
         ms_total = float(t.item())
     ms_step = ms_total / args.steps
     value = world * N * args.steps / (ms_total * 1e-3)
-    layer_ms = [float(np.mean([evs[s][i][0].elapsed_time(evs[s][i][1]) for s in range(args.steps)])) for i in range(nl)]
+    op_ms = [float(np.mean([evs[s][k][0].elapsed_time(evs[s][k][1]) for s in range(args.steps)])) for k in range(nops)]
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region, chunk-pipelined over streams ----
     nchunk = 4 if N % 4 == 0 else 1
@@ -274,7 +324,29 @@ def run_ours(args, specs, label):
     h2d = sum(h.numel() * 4 for h in host_in)
     d2h = sum(h.numel() * 4 for h in host_out)
 
+    if args.train:
+        h2d = sum(L["x"].numel() * 4 + L["dy"].numel() * 4 for L in layers)
+        d2h = sum(L["dx"].numel() * 4 for L in layers) + flat.numel() * 4
+        host_flat = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
+
     def e2e_step():
+        if args.train:
+            # host bottom + top_diff in, bottom_diff + the reduced flat gradient out; one stream per layer, round robin
+            for i, L in enumerate(layers):
+                st = streams[i % len(streams)]
+                with torch.cuda.stream(st):
+                    L["x"].copy_(host_in[2 * i], non_blocking=True)
+                    L["dy"].copy_(host_in[2 * i + 1], non_blocking=True)
+                    L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"], stream=st)
+                    L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"], accumulate=False, stream=st)
+                    L["plan"].backward_data(L["dy"], L["dx"], stream=st)
+                    host_out[2 * i + 1].copy_(L["dx"], non_blocking=True)
+            for st in streams:
+                st.synchronize()
+            exchange()
+            host_flat.copy_(flat, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
         k = 0
         for i, L in enumerate(layers):
             for c in range(nchunk):
@@ -308,32 +380,36 @@ def run_ours(args, specs, label):
         return
 
     # ---- roofline of the dominant kernel (largest share of the step) ----
-    dom = int(np.argmax(layer_ms))
-    L = layers[dom]
-    t_meas = layer_ms[dom] * 1e-3
+    kernel_of = {"fwd": lambda L: L["plan"].kernel_name, "bwd_weight": lambda L: "sconv_tile_bwdw(" + L["plan"].kernel_name + ")",
+                 "bwd_data": lambda L: "sconv_tile_fwd_on_transposed(" + L["plan"].kernel_name + ")"}
+    dom = int(np.argmax(op_ms))
+    L = layers[ops[dom][0]]
+    dom_kernel = kernel_of[ops[dom][1]](L)
+    t_meas = op_ms[dom] * 1e-3
     t_fma = L["flops"] / (fp32_peak * 1e12)
     t_hbm = L["bytes"] / (hbm_peak * 1e9)
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(L["spec"].name, {}).get(L["plan"].kernel_name)
+            traffic = json.load(open(tp)).get(L["spec"].name, {}).get(dom_kernel)
         except Exception:
             traffic = None
-    roofline = {"bound": "fp32_fma" if t_fma >= t_hbm else "hbm", "kernel": L["plan"].kernel_name,
+    roofline = {"bound": "fp32_fma" if t_fma >= t_hbm else "hbm", "kernel": dom_kernel, "op": ops[dom][1],
                 "layer": L["spec"].name, "achieved": L["flops"] / t_meas / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": max(t_fma, t_hbm) / t_meas,
                 "peak_source": "FP32 FMA: measured live by escort_measure_fp32_peak (best of FFMA / FFMA2 "
                                "register-resident loops); HBM: " + hbm_src,
                 "alg_flops_per_launch": L["flops"], "alg_bytes_per_launch": L["bytes"],
-                "launch_ms": layer_ms[dom], "hbm_achieved_gbs": L["bytes"] / t_meas / 1e9, "hbm_peak_gbs": hbm_peak,
+                "launch_ms": op_ms[dom], "hbm_achieved_gbs": L["bytes"] / t_meas / 1e9, "hbm_peak_gbs": hbm_peak,
                 "traffic": traffic, "fp32_peaks_tflops": fp32_peaks}
     per_layer = []
-    for i, Lr in enumerate(layers):
+    for k, (i, kind, _) in enumerate(ops):
+        Lr = layers[i]
         tf, th = Lr["flops"] / (fp32_peak * 1e12), Lr["bytes"] / (hbm_peak * 1e9)
-        per_layer.append({"layer": Lr["spec"].name, "kernel": Lr["plan"].kernel_name, "ms": layer_ms[i],
-                          "images_per_s": N / (layer_ms[i] * 1e-3), "tflops": Lr["flops"] / layer_ms[i] / 1e9,
-                          "roofline_frac": max(tf, th) / (layer_ms[i] * 1e-3), "nnz": int(Lr["plan"].nnz)})
+        per_layer.append({"layer": Lr["spec"].name, "op": kind, "kernel": kernel_of[kind](Lr), "ms": op_ms[k],
+                          "images_per_s": N / (op_ms[k] * 1e-3), "tflops": Lr["flops"] / op_ms[k] / 1e9,
+                          "roofline_frac": max(tf, th) / (op_ms[k] * 1e-3), "nnz": int(Lr["plan"].nnz)})
 
     # ---- cpu_baseline (N = 1 only): the reference's CPU path on this host, bounded sample ----
     cpu = None
@@ -343,7 +419,8 @@ def run_ours(args, specs, label):
             ips, ms, threads, kind = cpu_reference_run(specs, sample, 3, 1)
             cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
                    "sample": "%d of %d images x 3 steps through all %d layers (reference CPU direct sconv, "
-                             "OpenMP over images)" % (sample, N, nl)}
+                             "OpenMP over images)%s" % (sample, N, nl, "; forward only -- the reference's CPU backward is "
+                             "im2col + BLAS GEMM, which this image cannot build" if args.train else "")}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
 
@@ -351,13 +428,17 @@ def run_ours(args, specs, label):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": label, "batch_per_gpu": N, "global_batch": N * world, "parallelism": "batch-shard x%d, "
-                       "no data-path collective" % world, "epilogue": "bias+ReLU fused",
+                       "no data-path collective" % world if not args.train else
+                       "batch-shard x%d, NCCL all-reduce of the flat CSR-ordered gradient (%d floats) + 1/N scale" % (world, flat.numel()),
+                       "epilogue": "bias+ReLU fused" if not args.train else "bias fused (training step: no ReLU)",
                        "l2": "inputs+outputs of one step (%.0f MB) exceed the 126 MB L2, so every step re-reads HBM"
                              % (sum(Lr["bytes"] for Lr in layers) / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": "pinned host -> device, C-ABI forward, device -> pinned host; %d-image chunks over 4 streams"
-                           % cs},
-            "gpu_launches": nl * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+                    "how": ("pinned host -> device, C-ABI forward, device -> pinned host; %d-image chunks over 4 streams" % cs)
+                           if not args.train else "pinned host bottom + top_diff -> device, C-ABI forward + backward_weight + "
+                           "backward_data per layer (4 streams), gradient exchange, bottom_diff + flat gradient -> pinned host"},
+            "gpu_launches": (nops + (sum(1 for L in layers if L["b"] is not None) + nl + (1 if world > 1 else 0)
+                                     if args.train else 0)) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
             "layers": per_layer}
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -374,10 +455,13 @@ def main():
     ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = the full batch)")
     ap.add_argument("--variant", type=int, default=None, help="force a forward variant instead of autotuning")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--train", action="store_true",
+                    help="step = forward + masked backward (weight, data, bias) of every layer + the gradient all-reduce "
+                         "(BASELINE.json configs[3]); default: forward only")
     ap.add_argument("--tune-cache", default=None, help="JSON file caching the autotuned (variant, layout) per layer")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    specs, label = _workload(args.workload)
+    specs, label = _workload(args.workload, args.train)
     if args.impl == "reference":
         run_reference(args, specs, label)
     else:

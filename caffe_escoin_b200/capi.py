@@ -24,6 +24,7 @@ class Geom(C.Structure):
 EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
            "escort_plan_destroy", "escort_plan_nnz", "escort_plan_kernel_name", "escort_plan_describe",
            "escort_plan_set_variant", "escort_plan_set_config", "escort_plan_get_config", "escort_plan_autotune",
+           "escort_plan_autotune_backward",
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_measure_fp32_peak",
            "escort_last_error", "escort_version"]
@@ -39,6 +40,7 @@ lib.escort_plan_set_variant.argtypes = [C.c_void_p, C.c_int]
 lib.escort_plan_set_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.escort_plan_get_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.escort_plan_autotune.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.escort_plan_autotune_backward.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 
 
@@ -162,6 +164,9 @@ class Plan:
 
     def autotune(self, num, stream=None):
         _check(lib.escort_plan_autotune(self.h, int(num), _stream(stream)), "escort_plan_autotune")
+
+    def autotune_backward(self, num, stream=None):
+        _check(lib.escort_plan_autotune_backward(self.h, int(num), _stream(stream)), "escort_plan_autotune_backward")
 
     def forward(self, bottom, bias=None, relu=False, top=None, stream=None):
         g = self.geom

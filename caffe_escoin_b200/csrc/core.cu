@@ -607,21 +607,18 @@ static int autotune_one(escort_plan *p, int num, cudaStream_t stream) {
 extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");
-  int rc = autotune_one(p, num, stream);
-  if (rc) return rc;
+  return autotune_one(p, num, stream);
+}
+
+extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune_backward: bad arguments");
   if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
-    rc = build_bwd_plan(p, stream);
+    int rc = build_bwd_plan(p, stream);
     if (rc) return rc;
   }
-  if (p->bwd) {
-    rc = autotune_one(p->bwd, num, stream);
-    if (rc) return rc;
-    if (!p->bwd->tile) {  // the generic forward kernel won the sub-plan's timing: keep the dedicated backward kernel
-      escort_plan_destroy(p->bwd);
-      p->bwd = nullptr;
-    }
-  }
-  return 0;
+  if (!p->bwd) return 0;
+  return autotune_one(p->bwd, num, stream);
 }
 
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,

@@ -565,7 +565,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
         }
     const int prog_bytes = ceil_div(max_region16 * 16, 128) * 128;
     stage_bytes = ceil_div(in_bytes, 128) * 128 + prog_bytes;
-    scratch_bytes = V.MODE >= 5 ? NCW * std::max(max_seg_taps, 1) * 128 : 0;
+    scratch_bytes = V.MODE >= 5 ? NCW * (max_seg_taps + 1) * 128 : 0;
     NS = (int)std::min<long>(std::max<long>(smem_budget - tab_bytes - scratch_bytes, 0L) / stage_bytes, 4L);
     if (NS >= 3 || (NS >= 2 && CI == 1)) {
       prog.resize(words.size() / 4);
@@ -599,7 +599,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     pr.RO = 32 / lpr;
   }
   pr.scratch_off = pr.stage0_off + NS * stage_bytes;
-  pr.scratch_rows = std::max(max_seg_taps, 1);
+  pr.scratch_rows = max_seg_taps + 1;  // + the dummy row 0
   tp->smem_bytes = (size_t)pr.stage0_off + (size_t)NS * stage_bytes + (size_t)scratch_bytes;
   tp->nrecords = prog.size() * 2;
 

@@ -408,7 +408,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + 8 * s);  // the stage is no longer read: the sums live in the scratch rows
         for (unsigned k = lane; k < ntaps; k += 32) {
-          const float *row = scratch + (size_t)k * 32;
+          const float *row = scratch + (size_t)(k + 1) * 32;  // row 0 is the handler chain's dummy row
           float sum = 0.f;
 #pragma unroll 8
           for (int l = 0; l < 32; ++l) sum += row[(l + lane) & 31];  // rotated: one bank per lane

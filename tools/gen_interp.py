@@ -301,13 +301,17 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
     L = []
     a = L.append
     a("{")
-    a(".reg .f32 x<%d>, s<4>;" % NX)
+    a(".reg .f32 x<%d>, s<4>, r<2>;" % NX)
     a(".reg .b32 pc, pp, off, noff, t, t2, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
     a(".reg .pred p, pr<3>, pt<%d>;" % KW)
     # operands: %0 = taps executed (out), %1.. = dy tile, then prog, lane_base, pitch_bytes, scratch (lane's column)
     I0 = 1
     a("mov.u32 pc, %%%d;" % (I0 + NOPS))
+    # the combine (3 adds + store) of a tap is deferred to the head of the NEXT executed tap, where it overlaps that
+    # tap's FMAs instead of stalling on its own dependent adds; row 0 of the scratch is a dummy for the first "pending"
     a("mov.u32 pp, %%%d;" % (I0 + NOPS + 3))
+    for k in range(4):
+        a("mov.f32 s%d, 0f00000000;" % k)
     a("ld.shared.b32 off, [pc];")
     for k in range(NW):
         a("ld.shared.b32 m%d, [pc+%d];" % (k, 4 + 4 * k))
@@ -372,6 +376,11 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
             c = (o * KH + kh) * KW + kw
             if KW > 1:
                 a("@!pt%d bra.uni WH%dE;" % (kw, c))
+            a("add.rn.f32 r0, s0, s1;")
+            a("add.rn.f32 r1, s2, s3;")
+            a("add.rn.f32 r0, r0, r1;")
+            a("st.shared.f32 [pp], r0;")
+            a("add.u32 pp, pp, 128;")
             n = 0
             for ty in range(TY):
                 for tx in range(TX):
@@ -382,11 +391,6 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
                     else:
                         a("fma.rn.f32 s%d, %%%d, x%d, s%d;" % (n % 4, I0 + acc, xi, n % 4))
                     n += 1
-            a("add.rn.f32 s0, s0, s1;")
-            a("add.rn.f32 s2, s2, s3;")
-            a("add.rn.f32 s0, s0, s2;")
-            a("st.shared.f32 [pp], s0;")
-            a("add.u32 pp, pp, 128;")
             a("WH%dE:" % c)
     a("WRR%d:" % NR)
     a("mov.b32 off, noff;")
@@ -394,6 +398,10 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
         a("mov.b32 m%d, nm%d;" % (k, k))
     a("bra.uni WLOOP;")
     a("WDONE:")
+    a("add.rn.f32 r0, s0, s1;")
+    a("add.rn.f32 r1, s2, s3;")
+    a("add.rn.f32 r0, r0, r1;")
+    a("st.shared.f32 [pp], r0;")
     a("sub.u32 pp, pp, %%%d;" % (I0 + NOPS + 3))
     a("shr.u32 %0, pp, 7;")
     a("}")
@@ -410,7 +418,7 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
     NTW = NCW + (4 if CREGS else NLW)
     src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;" % (NCW, NLW, NTW, CREGS, 5 if PLAN == "a" else 6))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
-    src.append("  // returns the number of taps executed (= scratch rows written)")
+    src.append("  // returns the number of taps executed; their partials are in scratch rows 1 .. ntaps (row 0 is a dummy)")
     src.append("  __device__ __forceinline__ static unsigned run_w(const float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
     src.append("                                                   unsigned pitch_bytes, unsigned scratch) {")
     src.append("    unsigned ntaps;")

@@ -40,6 +40,8 @@ for arg in sys.argv[1:]:
     t_f = timeit(lambda: plan.forward(x, None, top=y))
     t_d = timeit(lambda: plan.backward_data(dy, dx))
     t_w = timeit(lambda: plan.backward_weight(x, dy, wd_dense=wd, accumulate=False))
+    wd.zero_()   # the dense diff accumulates (Caffe's contract): one clean pass for the cross-check
+    plan.backward_weight(x, dy, wd_dense=wd, accumulate=False)
     # cross-check against the generic kernels
     os.environ["ESCORT_GENERIC_BACKWARD"] = "1"
     dx2 = torch.empty_like(x)

@@ -130,12 +130,16 @@ static int choose_variant(const escort_geom &g, double density, int Ho) {
   const char *prefs[4] = {nullptr, nullptr, nullptr, nullptr};
   if (k == 3 && g.kernel_w == 3 && s == 1) {
     if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_sar_o3_y7_x4_k3x3_s1_w12_r152";
-    else if (Ho >= 14) prefs[0] = "sconv_tile_sb_o3_y7_x4_k3x3_s1_w12_r152";
+    else if (Ho >= 20) prefs[0] = "sconv_tile_sbr_o3_y7_x4_k3x3_s1_w12_r152";
+    else if (Ho >= 14) prefs[0] = "sconv_tile_o4_y4_x4_k3x3_s1_p2_w8_r232";
     else if (density < 0.2) prefs[0] = "sconv_tile_sbr_o4_y4_x4_k3x3_s1_w12_r152";
     else prefs[0] = "sconv_tile_sb_o6_y4_x4_k3x3_s1_w12_r152";
     prefs[1] = "sconv_tile_sb_o4_y4_x4_k3x3_s1_w12_r152";
   } else if (k == 5 && g.kernel_w == 5 && s == 1) {
-    prefs[0] = "sconv_tile_sb_o4_y4_x4_k5x5_s1_w12_r152";
+    // 100 handlers: code size decides (instruction-cache misses), so two output channels per lane and, where the
+    // batch allows, the packed two-image FFMA2 handlers (half the instructions per FMA)
+    prefs[0] = Ho >= 13 ? "sconv_tile_rbj_o2_y4_x4_k5x5_s1_p2_w8_r232" : "sconv_tile_sbr_o2_y4_x4_k5x5_s1_w12_r152";
+    prefs[1] = "sconv_tile_sbr_o2_y4_x4_k5x5_s1_w12_r152";
   } else if (k == 1 && g.kernel_w == 1 && s == 1) {
     prefs[0] = Ho >= 14 ? "sconv_tile_sb_o6_y7_x4_k1x1_s1_w8_r232" : "sconv_tile_sb_o8_y2_x4_k1x1_s1_w16_r104";
   } else if (k == 3 && g.kernel_w == 3 && s == 2) {
@@ -165,7 +169,7 @@ int tile_bwdw_variant(const escort_plan *plan) {
     if (plan->Ho >= 14) pref = tma_w ? "sconv_tile_wa_o3_y7_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o3_y7_x4_k3x3_s1_w12_r152";
     else pref = density < 0.2 ? "sconv_tile_wb_o4_y4_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o6_y4_x4_k3x3_s1_w12_r152";
   } else if (k == 5 && g.kernel_w == 5) {
-    pref = "sconv_tile_wb_o4_y4_x4_k5x5_s1_w12_r152";
+    pref = "sconv_tile_wb_o2_y4_x4_k5x5_s1_w12_r152";
   } else if (k == 1 && g.kernel_w == 1) {
     pref = "sconv_tile_wb_o8_y2_x4_k1x1_s1_w16_r104";
   }

@@ -71,6 +71,10 @@ SIEVE_R = [
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
+    # 5x5 with fewer output channels per lane: 100 handlers of o4 are ~35 KB of code and the instruction cache thrashes
+    # (no_instruction = 4 stall cycles per issue on AlexNet conv2); o2 / o3 halve it at the price of more patch loads
+    (2, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
+    (3, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
 ]
 
 
@@ -283,6 +287,8 @@ BWDW = [
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
     (8, 2, 4, 1, 1, 1, 1, 16, 4, 104, "b"),
+    (2, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
+    (3, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
 ]
 
 
@@ -446,6 +452,7 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
 ROWS = [
     # 3x3, two images per lane (FFMA2), patch-aligned rows
     (4, 4, 4, 3, 3, 1, 2, 8, 4, 232, "b", "j"),
+    (2, 4, 4, 5, 5, 1, 2, 8, 4, 232, "b", "j"),
 ]
 
 

@@ -124,6 +124,7 @@ class ConvolutionLayer {
 
   // Dense -> CSR per group (bit-exact with caffe_cpu_sparse_dense2csr), stretch, then the plan the forward executes.
   // Called where Net::CopyTrainedLayersFrom calls it (src/caffe/net.cpp:819), i.e. after the weights are in blobs_[0].
+  bool tune_backward_ = false;  // training hosts (phase TRAIN) also tune the backward-data kernel
   void WeightAlign(int tune_batch = 0) {
     const ConvolutionParameter &p = param_;
     const int M = p.num_output / p.group, N = (channels_ / p.group) * p.kernel_h * p.kernel_w;
@@ -143,6 +144,8 @@ class ConvolutionLayer {
                              nullptr),
           "escort_plan_create");
     if (tune_batch > 0) check(escort_plan_autotune(plan_, tune_batch, nullptr), "escort_plan_autotune");
+    if (tune_batch > 0 && tune_backward_)
+      check(escort_plan_autotune_backward(plan_, tune_batch, nullptr), "escort_plan_autotune_backward");
   }
 
   // conv_layer.cu:8-40: in SCONV / SCONV_PAR mode the whole batch, all groups, bias (and ReLU for ConvolutionReLU).

@@ -133,7 +133,7 @@ static int choose_variant(const escort_geom &g, double density, int Ho) {
     else if (Ho >= 20) prefs[0] = "sconv_tile_sbr_o3_y7_x4_k3x3_s1_w12_r152";
     else if (Ho >= 14) prefs[0] = "sconv_tile_o4_y4_x4_k3x3_s1_p2_w8_r232";
     else if (density < 0.2) prefs[0] = "sconv_tile_sbr_o4_y4_x4_k3x3_s1_w12_r152";
-    else prefs[0] = "sconv_tile_sb_o6_y4_x4_k3x3_s1_w12_r152";
+    else prefs[0] = "sconv_tile_sbr_o5_y4_x4_k3x3_s1_w12_r152";
     prefs[1] = "sconv_tile_sb_o4_y4_x4_k3x3_s1_w12_r152";
   } else if (k == 5 && g.kernel_w == 5 && s == 1) {
     // 100 handlers: code size decides (instruction-cache misses), so two output channels per lane and, where the
@@ -167,7 +167,7 @@ int tile_bwdw_variant(const escort_plan *plan) {
   const char *pref = nullptr;
   if (k == 3 && g.kernel_w == 3) {
     if (plan->Ho >= 14) pref = tma_w ? "sconv_tile_wa_o3_y7_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o3_y7_x4_k3x3_s1_w12_r152";
-    else pref = density < 0.2 ? "sconv_tile_wb_o4_y4_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o6_y4_x4_k3x3_s1_w12_r152";
+    else pref = density < 0.2 ? "sconv_tile_wb_o4_y4_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o5_y4_x4_k3x3_s1_w12_r152";
   } else if (k == 5 && g.kernel_w == 5) {
     pref = "sconv_tile_wb_o2_y4_x4_k5x5_s1_w12_r152";
   } else if (k == 1 && g.kernel_w == 1) {
@@ -250,6 +250,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int PY = ceil_div(Ho, TY), PX = ceil_div(Wo, TX);
   const int per_vec = 4 / PAIR;
   const int PC = (TX - 1) * S + KW;
+  if ((TX * S * PAIR) % 4 != 0 && PX > 1) return 0;  // the lanes' 128-bit patch loads need 16-byte aligned tile origins
   // columns the patch-aligned load plan touches (128-bit loads with a 64-bit tail; PAIR 2: exactly PC positions)
   const int XW = PAIR == 2 ? PC : (PC % 4 == 0 ? PC : (PC % 4 <= 2 ? PC - PC % 4 + 2 : PC - PC % 4 + 4));
   // TMA staging (cp.async.bulk.tensor with out-of-bounds zero fill = the halo) needs 16-byte global strides and a

@@ -329,6 +329,40 @@ def test_backward_vs_oracle(capi, po, case, generic_bwd, monkeypatch):
     assert po.rel_l2(wd_csr.cpu().numpy(), 2.0 * got) < TOL
 
 
+def test_autotune_forward_and_backward(capi, po):
+    """Plan-time autotune (cuDNN-find idiom) of the forward and of the backward-data sub-plan keeps results correct, and a
+    training loop (refresh -> forward -> backward) on the tuned plan follows the updated weights in both directions."""
+    torch = _torch()
+    from caffe_escoin_b200 import workloads as wl
+    spec = wl.RESNET50[3]._replace(N=6, Cin=32, Cout=48)        # 28x28: TMA-staged kernels are candidates
+    d = wl.make_layer_data(spec, 5)
+    g = po.Geom(spec.N, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+    geom = capi_geom(capi, g)
+    w = to_dev(d["w"])
+    csr = capi.weight_align(w, geom)
+    plan = capi.Plan(geom, csr)
+    plan.autotune(spec.N)
+    plan.autotune_backward(spec.N)
+    v, r = plan.get_config()
+    assert v >= 0 and r >= 0
+    mask = (w != 0).float()
+    for it in range(2):
+        w = (w + 0.03 * torch.randn_like(w) * mask).contiguous()
+        plan.refresh_values(w, csr["values"])
+        y = plan.forward(to_dev(d["x"]), None)
+        dy = torch.rand_like(y) * 2 - 1
+        dx = plan.backward_data(dy)
+        wd = torch.zeros_like(w)
+        plan.backward_weight(to_dev(d["x"]), dy, wd_dense=wd)
+        torch.cuda.synchronize()
+        wn = w.cpu().numpy()
+        y_or = po.conv_forward(d["x"], po.weight_align(wn, g), g, None)
+        assert po.rel_l2(y.cpu().numpy(), y_or) < TOL
+        wd_o, _, dx_o = po.conv_backward(d["x"], dy.cpu().numpy(), wn, g, mask_only=True, want_b=False)
+        assert po.rel_l2(dx.cpu().numpy(), dx_o) < TOL
+        assert po.rel_l2(wd.cpu().numpy(), wd_o) < TOL
+
+
 def test_refresh_values_after_update(capi, po):
     """Masked SGD step: update dense weights at mask positions, re-gather CSR values, forward must follow."""
     torch = _torch()

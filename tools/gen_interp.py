@@ -70,6 +70,7 @@ SIEVE_R = [
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", 1),
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
+    (5, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 512 channels / 5 -> 9 channel-block groups: 288 units = 2 full waves of 148
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
     # 5x5 with fewer output channels per lane: 100 handlers of o4 are ~35 KB of code and the instruction cache thrashes
     # (no_instruction = 4 stall cycles per issue on AlexNet conv2); o2 / o3 halve it at the price of more patch loads
@@ -285,6 +286,7 @@ BWDW = [
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b"),
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
+    (5, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),
     (8, 2, 4, 1, 1, 1, 1, 16, 4, 104, "b"),
     (2, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b"),

@@ -143,7 +143,8 @@ static int choose_variant(const escort_geom &g, double density, int Ho) {
   } else if (k == 1 && g.kernel_w == 1 && s == 1) {
     prefs[0] = Ho >= 14 ? "sconv_tile_sb_o6_y7_x4_k1x1_s1_w8_r232" : "sconv_tile_sb_o8_y2_x4_k1x1_s1_w16_r104";
   } else if (k == 3 && g.kernel_w == 3 && s == 2) {
-    prefs[0] = "sconv_tile_sb_o4_y4_x4_k3x3_s2_w8_r232";
+    prefs[0] = Ho >= 14 ? "sconv_tile_sbr_o4_y4_x4_k3x3_s2_w8_r232" : "sconv_tile_sbr_o4_y2_x4_k3x3_s2_w12_r152";
+    prefs[1] = "sconv_tile_sb_o4_y4_x4_k3x3_s2_w8_r232";
   }
   for (const char *p : prefs)
     if (p) {

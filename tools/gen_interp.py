@@ -76,6 +76,9 @@ SIEVE_R = [
     # (no_instruction = 4 stall cycles per issue on AlexNet conv2); o2 / o3 halve it at the price of more patch loads
     (2, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
     (3, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
+    # stride 2
+    (4, 4, 4, 3, 3, 2, 1, 8, 4, 232, "b", 1),
+    (4, 2, 4, 3, 3, 2, 1, 12, 4, 152, "b", 1),
 ]
 
 

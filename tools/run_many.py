@@ -12,7 +12,7 @@ from caffe_escoin_b200 import capi, workloads as wl  # noqa: E402
 for arg in sys.argv[1:]:
     net, idx, vs = arg.split(":")
     idx = int(idx)
-    spec = wl.NETWORKS[net][idx]
+    spec = wl.sweep_specs(64)[idx] if net == "sweep" else wl.NETWORKS[net][idx]
     d = wl.make_layer_data(spec, idx)
     geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
     csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)

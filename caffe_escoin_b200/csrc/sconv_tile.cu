@@ -101,6 +101,8 @@ void tile_plan_free(TilePlan *tp) {
   cudaFree(tp->d_rtab);
   cudaFree(tp->d_prog_pos);
   cudaFree(tp->d_tapidx);
+  cudaFree(tp->d_tap_dense);
+  cudaFree(tp->d_tap_csr);
   delete tp;
 }
 
@@ -687,6 +689,11 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
   return 0;
 }
 
+__global__ void gather_idx_kernel(long n, const int *__restrict__ tapidx, const int *__restrict__ table, int *__restrict__ out) {
+  const long t = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = table[tapidx[t]];
+}
+
 __global__ void zero_at_kernel(long nnz, const int *__restrict__ idx, float *__restrict__ dst) {
   const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (j < nnz) dst[idx[j]] = 0.f;
@@ -699,8 +706,8 @@ int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_
   TilePlan *tp = plan->tile_w;
   TileParams prm = tp->prm;
   prm.n_igroups = ceil_div(num, prm.G);
-  prm.dense_idx = plan->d_dense_idx;
-  prm.csr_pos = plan->d_csr_pos;
+  prm.tap_dense = tp->d_tap_dense;
+  prm.tap_csr = tp->d_tap_csr;
   int nunits = (int)((size_t)prm.n_igroups * prm.nbands * prm.ngroups * prm.ogroups);
   const unsigned grid = (unsigned)std::min(nunits, tp->num_sms);
   const VariantDesc &V = kVariants[tp->vidx];
@@ -748,6 +755,17 @@ int tile_bwdw_build(escort_plan *plan, cudaStream_t stream) {
   plan->tile_w = plan->tile;
   plan->tile = fwd;
   plan->layout_rank = rank;
+  if (rc == 0 && plan->tile_w) {
+    // per-tap destinations (stream order), so that the flush needs one index load per tap instead of two dependent ones
+    TilePlan *tp = plan->tile_w;
+    const long n = plan->nnz;
+    ESCORT_CUDA(cudaMalloc((void **)&tp->d_tap_dense, std::max<long>(n, 1) * sizeof(int)));
+    ESCORT_CUDA(cudaMalloc((void **)&tp->d_tap_csr, std::max<long>(n, 1) * sizeof(int)));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_dense_idx, tp->d_tap_dense);
+    gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_csr_pos, tp->d_tap_csr);
+    ESCORT_LAUNCH_CHECK();
+  }
   return rc;
 }
 

@@ -43,8 +43,8 @@ struct TileParams {
   int scratch_off;         // byte offset of the scratch area in dynamic smem
   int scratch_rows;        // rows (taps) per warp = the longest segment of the plan
   const int *tapidx;       // stream-order tap -> row-major nonzero index
-  const int *dense_idx;    // nonzero -> index in the dense weight tensor   (filled per launch)
-  const int *csr_pos;      // nonzero -> position in the reference's CSR blob layout
+  const int *tap_dense;    // stream-order tap -> index in the dense weight tensor
+  const int *tap_csr;      // stream-order tap -> position in the reference's CSR blob layout
 };
 
 #ifndef ESCORT_TILE_DEVICE_ONLY
@@ -60,6 +60,7 @@ struct TilePlan {
   int2 *d_rtab;
   int *d_prog_pos;         // [nnz] row-major nonzero -> 4-byte word index of its weight in d_prog
   int *d_tapidx;           // W variants: stream-order tap -> row-major nonzero index
+  int *d_tap_dense, *d_tap_csr;  // W variants: stream-order tap -> destination in the dense / CSR-ordered gradient
   size_t nrecords;
   int num_sms;
 };
@@ -408,13 +409,21 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + 8 * s);  // the stage is no longer read: the sums live in the scratch rows
         for (unsigned k = lane; k < ntaps; k += 32) {
+          // destinations first: their L2 latency hides behind the row sum
+          const int jd = wd_dense ? __ldg(p.tap_dense + tapbase + k) : 0;
+          const int jc = wd_csr ? __ldg(p.tap_csr + tapbase + k) : 0;
           const float *row = scratch + (size_t)(k + 1) * 32;  // row 0 is the handler chain's dummy row
-          float sum = 0.f;
-#pragma unroll 8
-          for (int l = 0; l < 32; ++l) sum += row[(l + lane) & 31];  // rotated: one bank per lane
-          const int j = __ldg(p.tapidx + tapbase + k);
-          if (wd_dense) atomicAdd(wd_dense + __ldg(p.dense_idx + j), sum);
-          if (wd_csr) atomicAdd(wd_csr + __ldg(p.csr_pos + j), sum);
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+          for (int l = 0; l < 32; l += 4) {  // rotated: one bank per lane; four independent chains
+            s0 += row[(l + lane) & 31];
+            s1 += row[(l + 1 + lane) & 31];
+            s2 += row[(l + 2 + lane) & 31];
+            s3 += row[(l + 3 + lane) & 31];
+          }
+          const float sum = (s0 + s1) + (s2 + s3);
+          if (wd_dense) atomicAdd(wd_dense + jd, sum);
+          if (wd_csr) atomicAdd(wd_csr + jc, sum);
         }
         __syncwarp();
         if (++s == (unsigned)p.NS) {

@@ -380,8 +380,7 @@ def run_ours(args, specs, label):
         return
 
     # ---- roofline of the dominant kernel (largest share of the step) ----
-    kernel_of = {"fwd": lambda L: L["plan"].kernel_name, "bwd_weight": lambda L: "sconv_tile_bwdw(" + L["plan"].kernel_name + ")",
-                 "bwd_data": lambda L: "sconv_tile_fwd_on_transposed(" + L["plan"].kernel_name + ")"}
+    kernel_of = {k: (lambda L, k=k: L["plan"].kernel_names()[k]) for k in ("fwd", "bwd_weight", "bwd_data")}
     dom = int(np.argmax(op_ms))
     L = layers[ops[dom][0]]
     dom_kernel = kernel_of[ops[dom][1]](L)

@@ -147,9 +147,19 @@ class Plan:
         return lib.escort_plan_kernel_name(self.h).decode()
 
     def describe(self):
-        buf = C.create_string_buffer(512)
-        lib.escort_plan_describe(self.h, buf, 512)
+        buf = C.create_string_buffer(2048)
+        lib.escort_plan_describe(self.h, buf, 2048)
         return buf.value.decode()
+
+    def kernel_names(self):
+        """{'fwd': ..., 'bwd_data': ..., 'bwd_weight': ...}: kernels in use (backward entries once those plans exist)."""
+        parts = self.describe().split(" | ")
+        out = {"fwd": parts[0].split(" ")[0] if parts[0] != "generic" else "sconv_fwd_generic",
+               "bwd_data": "sconv_bwd_data_generic", "bwd_weight": "sconv_bwd_weight_generic"}
+        for p in parts[1:]:
+            k, v = p.split(": ", 1)
+            out[k] = v.split(" ")[0] + ("(transposed plan)" if k == "bwd_data" else "")
+        return out
 
     def set_variant(self, v):
         _check(lib.escort_plan_set_variant(self.h, int(v)), "escort_plan_set_variant")

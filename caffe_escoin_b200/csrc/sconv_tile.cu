@@ -903,19 +903,28 @@ extern "C" ESCORT_API int escort_interp_bench(int variant, int per_load, int act
 }
 
 // introspection for tests/bench: tiling summary as a string
+static int describe_tile(const TilePlan *tp, char *buf, int buflen) {
+  const TileParams &p = tp->prm;
+  return snprintf(buf, buflen,
+                  "%s%s G=%d BR=%d nbands=%d WP=%d WO=%d R=%d P=%d plane_f=%d CI=%d nchunks=%d nblk=%d ogroups=%d nslots=%d NS=%d "
+                  "stage=%dB smem=%zu records=%zu",
+                  tp->name, p.use_tma ? " tma" : "", p.G, p.BR, p.nbands, p.WP, p.WO, p.R, p.P, p.plane_f, p.CI, p.nchunks, p.nblk,
+                  p.ogroups, p.nslots, p.NS, p.stage_bytes, tp->smem_bytes, tp->nrecords);
+}
+
+// forward kernel + tiling; once the backward plans exist (first backward call / escort_plan_autotune_backward) also
+// " | bwd_data: <kernel + tiling>" and " | bwd_weight: <kernel + tiling>"
 extern "C" ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen) {
   if (!plan || !buf || buflen <= 0) return ESCORT_EINVAL;
-  if (!plan->tile) {
-    snprintf(buf, buflen, "generic");
-    return 0;
+  int n = plan->tile ? describe_tile(plan->tile, buf, buflen) : snprintf(buf, buflen, "generic");
+  if (plan->bwd && plan->bwd->tile && n > 0 && n < buflen - 16) {
+    n += snprintf(buf + n, buflen - n, " | bwd_data: ");
+    if (n < buflen) n += describe_tile(plan->bwd->tile, buf + n, buflen - n);
   }
-  const TilePlan *tp = plan->tile;
-  const TileParams &p = tp->prm;
-  snprintf(buf, buflen,
-           "%s%s G=%d BR=%d nbands=%d WP=%d WO=%d R=%d P=%d plane_f=%d CI=%d nchunks=%d nblk=%d ogroups=%d nslots=%d NS=%d "
-           "stage=%dB smem=%zu records=%zu",
-           tp->name, p.use_tma ? " tma" : "", p.G, p.BR, p.nbands, p.WP, p.WO, p.R, p.P, p.plane_f, p.CI, p.nchunks, p.nblk, p.ogroups, p.nslots,
-           p.NS, p.stage_bytes, tp->smem_bytes, tp->nrecords);
+  if (plan->tile_w && n > 0 && n < buflen - 16) {
+    n += snprintf(buf + n, buflen - n, " | bwd_weight: ");
+    if (n < buflen) n += describe_tile(plan->tile_w, buf + n, buflen - n);
+  }
   return 0;
 }
 

@@ -22,9 +22,10 @@ for arg in sys.argv[1:]:
     y = torch.empty((spec.N, spec.Cout, plan.Ho, plan.Wo), device="cuda")
     flops, _ = wl.alg_work(spec, plan.nnz)
     yref = None
-    for v in [int(t) for t in vs.split(",")]:
+    for vt in vs.split(","):
+        v, rank = (int(t) for t in (vt.split("r") + ["0"])[:2])   # "4r2" = variant 4, tiling candidate 2
         try:
-            plan.set_variant(v)
+            plan.set_config(v, rank)
         except capi.EscortError:
             print("%s v%d unsupported" % (spec.name, v))
             continue

@@ -185,6 +185,8 @@ def run_ours(args, specs, label):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout; this program prints ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     if not os.path.exists(os.path.join(ROOT, "caffe_escoin_b200", "libescort_b200.so")):
         if rank == 0:

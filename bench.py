@@ -185,9 +185,18 @@ def run_ours(args, specs, label):
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"   # NCCL's version banner goes to stdout; this program prints ONE JSON line there
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL prints its version banner to stdout when the first communicator comes up; stdout carries ONE JSON line,
+        # so the bring-up (init + first collective) runs with fd 1 pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            os.dup2(saved, 1)
+            os.close(saved)
     if not os.path.exists(os.path.join(ROOT, "caffe_escoin_b200", "libescort_b200.so")):
         if rank == 0:
             ge.build()

@@ -84,7 +84,8 @@ void tile_plan_free(TilePlan *tp);
 int tile_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,
                  cudaStream_t stream);
 int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream);
-int tile_bwdw_build(escort_plan *plan, cudaStream_t stream);
+int tile_bwdw_build(escort_plan *plan, cudaStream_t stream, int variant = 0);
+int tile_bwdw_autotune(escort_plan *plan, int num, cudaStream_t stream);
 int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_diff, float *wd_dense, float *wd_csr,
               int accumulate, cudaStream_t stream);
 const char *tile_kernel_name(const TilePlan *tp);

@@ -617,8 +617,12 @@ extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_str
     int rc = build_bwd_plan(p, stream);
     if (rc) return rc;
   }
-  if (!p->bwd) return 0;
-  return autotune_one(p->bwd, num, stream);
+  if (p->bwd) {
+    int rc = autotune_one(p->bwd, num, stream);
+    if (rc) return rc;
+  }
+  if (getenv("ESCORT_GENERIC_BACKWARD") || getenv("ESCORT_BWDW_VARIANT")) return 0;
+  return tile_bwdw_autotune(p, num, stream);  // and the backward-weight (W) variant
 }
 
 extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom, const float *bias, int fuse_relu,

@@ -742,10 +742,15 @@ int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_
   return 0;
 }
 
-// build plan->tile_w (the backward-weight plan) with the default W variant; leaves it null if none applies
-int tile_bwdw_build(escort_plan *plan, cudaStream_t stream) {
-  const int v = tile_bwdw_variant(plan);
+// build plan->tile_w (the backward-weight plan) with the given W variant (1-based; <= 0: the default for the geometry);
+// leaves it null if none applies
+int tile_bwdw_build(escort_plan *plan, cudaStream_t stream, int variant) {
+  const int v = variant > 0 ? variant : tile_bwdw_variant(plan);
   if (v <= 0) return 0;
+  if (plan->tile_w) {
+    tile_plan_free(plan->tile_w);
+    plan->tile_w = nullptr;
+  }
   TilePlan *fwd = plan->tile;
   const int rank = plan->layout_rank;
   plan->layout_rank = 0;
@@ -767,6 +772,62 @@ int tile_bwdw_build(escort_plan *plan, cudaStream_t stream) {
     ESCORT_LAUNCH_CHECK();
   }
   return rc;
+}
+
+// plan-time selection of the backward-weight variant by measurement: every W variant of the layer's kernel size is
+// built and timed on scratch tensors of `num` images; the fastest stays in plan->tile_w
+int tile_bwdw_autotune(escort_plan *plan, int num, cudaStream_t stream) {
+  const escort_geom &g = plan->g;
+  if (g.stride_h != 1 || g.stride_w != 1 || g.dilation_h != 1 || g.dilation_w != 1 || plan->nnz == 0) return 0;
+  const size_t in_elems = (size_t)num * g.channels * g.height * g.width;
+  const size_t out_elems = (size_t)num * g.num_output * plan->Ho * plan->Wo;
+  float *x = nullptr, *dy = nullptr, *wd = nullptr;
+  ESCORT_CUDA(cudaMalloc((void **)&x, in_elems * sizeof(float)));
+  cudaError_t e = cudaMalloc((void **)&dy, out_elems * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc((void **)&wd, (size_t)g.num_output * (g.channels / g.group) * g.kernel_h * g.kernel_w * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(x);
+    cudaFree(dy);
+    return cuda_fail(e, "cudaMalloc(autotune scratch)", __FILE__, __LINE__);
+  }
+  cudaMemsetAsync(x, 0, in_elems * sizeof(float), stream);
+  cudaMemsetAsync(dy, 0, out_elems * sizeof(float), stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  int best_v = 0;
+  float best_ms = 1e30f;
+  for (int v = 1; v <= kNumVariants; ++v) {
+    const VariantDesc &V = kVariants[v - 1];
+    if (V.MODE < 5 || V.KH != g.kernel_h || V.KW != g.kernel_w) continue;
+    if (tile_bwdw_build(plan, stream, v) != 0 || !plan->tile_w) continue;
+    float ms_best = 1e30f;
+    bool ok = true;
+    for (int it = 0; it < 3 && ok; ++it) {
+      cudaEventRecord(e0, stream);
+      ok = tile_bwdw(plan, num, x, dy, wd, nullptr, 1, stream) == 0;
+      cudaEventRecord(e1, stream);
+      if (cudaEventSynchronize(e1) != cudaSuccess) ok = false;
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, e0, e1);
+      if (it > 0 && ms < ms_best) ms_best = ms;
+    }
+    if (ok && ms_best < best_ms) {
+      best_ms = ms_best;
+      best_v = v;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(x);
+  cudaFree(dy);
+  cudaFree(wd);
+  cudaGetLastError();
+  plan->tile_w_tried = 1;
+  int rc = tile_bwdw_build(plan, stream, best_v);  // best_v == 0: the default
+  if (rc) return rc;
+  ESCORT_CUDA(cudaStreamSynchronize(stream));
+  return 0;
 }
 
 __global__ void tile_refresh_kernel(long nnz, const float *__restrict__ w_dense, const int *__restrict__ dense_idx,

@@ -113,7 +113,7 @@ ESCORT_API int escort_plan_get_config(const escort_plan *plan, int *variant_host
  * fastest (plan-time selection, like cuDNN's find); synchronises `stream`.  Optional: without it the plan
  * uses a static default. */
 ESCORT_API int escort_plan_autotune(escort_plan *plan, int num, escort_stream_t stream);
-/* the same for the backward-data kernel (stride-1 layers run it as a forward plan over the transposed, rotated
+/* the same for the backward kernels: the backward-weight variant, and the backward-data kernel (stride-1 layers run it as a forward plan over the transposed, rotated
  * weights -- ConvolutionLayer::Backward_gpu's backward_gpu_gemm + col2im, src/caffe/layers/conv_layer.cu:64-68);
  * a no-op for geometries that use the generic backward kernel.  Training hosts call it once after WeightAlign. */
 ESCORT_API int escort_plan_autotune_backward(escort_plan *plan, int num, escort_stream_t stream);

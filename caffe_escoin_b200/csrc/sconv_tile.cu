@@ -388,7 +388,10 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   std::vector<int2> rtab;
   std::vector<int> prog_pos, tapidx;
   int nchunks = 0, NS = 0, in_bytes = 0, stage_bytes = 0, max_region16 = 0, slot_f = 0, max_seg_taps = 0, scratch_bytes = 0;
-  if (V.MODE >= 5) CI = std::max(1, std::min(CI, 6));  // short chunks keep the per-warp scratch rows small
+  if (V.MODE >= 5) {  // short chunks keep the per-warp scratch rows small
+    const char *e = getenv("ESCORT_W_CI");
+    CI = std::max(1, std::min(CI, e ? atoi(e) : 10));
+  }
   for (int attempt = 0; attempt < 8; ++attempt) {
     nchunks = ceil_div(Cg, CI);
     CI = ceil_div(Cg, nchunks);  // even out the chunks

@@ -1,0 +1,35 @@
+#!/bin/bash
+# How profiles/r01_final_* were produced (each block is one `gpurun -- 'bash tools/reproduce_profiles.sh <block>'` call).
+set -x
+O=gpurun_out/final
+mkdir -p $O
+case "${1:-bench}" in
+bench)   # 1 GPU: parity tests, the bench lines, the reference arm
+  python -m pytest tests -x -q -m gpu > $O/pytest_gpu.log 2>&1; tail -2 $O/pytest_gpu.log
+  python bench.py --steps 10 --warmup 3 --tune-cache $O/tune_alexnet.json > $O/bench_alexnet.json
+  python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_alexnet_reference.json
+  for w in resnet50 googlenet lenet; do python bench.py --workload $w --steps 5 --warmup 3 --no-cpu > $O/bench_$w.json; done
+  for w in resnet50 alexnet; do python bench.py --workload $w --train --steps 5 --warmup 3 --no-cpu > $O/bench_${w}_train.json; done
+  ;;
+ncu)     # 1 GPU: launch list of the default bench command + one full capture per kernel of the step
+  python bench.py --steps 2 --warmup 3 --no-cpu --tune-cache $O/tune_alexnet.json > /dev/null
+  ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ncu_launches_alexnet_bench.csv \
+      python bench.py --steps 2 --warmup 3 --no-cpu --tune-cache $O/tune_alexnet.json > $O/ncu_launch.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:sconv_tile_kernel -s 12 -c 4 -f -o $O/ncu_full_alexnet_step \
+      python bench.py --steps 2 --warmup 3 --no-cpu --tune-cache $O/tune_alexnet.json > $O/ncu_full.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:sconv_tile_bwdw -s 1 -c 1 -f -o $O/ncu_full_res2a_bwdw \
+      python tools/run_bwd.py resnet50:0 > $O/ncu_bwdw.log 2>&1
+  # then, on the CPU box: python tools/ncu_summary.py $O/<rep>.ncu-rep --top 16 > profiles/r01_final_ncu_<...>_stalls.txt
+  ;;
+sweep)   # 1 GPU: BASELINE configs[4]
+  python tools/sweep.py > $O/sweep.jsonl
+  python tools/sweep.py --autotune > $O/sweep_autotuned.jsonl
+  ;;
+multi)   # N GPUs (gpurun --gpus N): the same bench under torchrun
+  N=${2:-2}
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 \
+      bench.py --gpus $N --steps 10 --warmup 3 > $O/bench_alexnet_${N}gpu.json
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29522 \
+      bench.py --gpus $N --workload resnet50 --train --steps 5 --warmup 3 > $O/bench_resnet50_train_${N}gpu.json
+  ;;
+esac

@@ -36,7 +36,7 @@ namespace escort {
 // variant table
 // ------------------------------------------------------------------------------------------------------
 struct VariantDesc {
-  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE;
+  int OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL;
   const char *name;
   const void *kernel;
   const void *bench;
@@ -44,7 +44,7 @@ struct VariantDesc {
 };
 
 // one translation unit per variant (tile_variant.cu compiled with -DESCORT_VARIANT_ID=k) exports these
-#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
+#define ESCORT_VARIANT_DECL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL) \
   const void *tile_variant_kernel_##ID();                         \
   const void *tile_variant_bench_##ID();                          \
   const void *tile_variant_bwdw_##ID();                           \
@@ -55,8 +55,8 @@ static const VariantDesc *variants() {
   static VariantDesc tab[kNumVariants];
   static bool init = false;
   if (!init) {
-#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE) \
-  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID(), tile_variant_bwdw_##ID()};
+#define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL) \
+  tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID(), tile_variant_bwdw_##ID()};
     ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
     init = true;
   }
@@ -131,7 +131,7 @@ static int choose_variant(const escort_geom &g, double density, int Ho) {
   const bool tma_w = g.width % 4 == 0 && g.pad_w == (k - 1) / 2 && tma_encoder() != nullptr && !getenv("ESCORT_NO_TMA");
   const char *prefs[4] = {nullptr, nullptr, nullptr, nullptr};
   if (k == 3 && g.kernel_w == 3 && s == 1) {
-    if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_sar_o3_y7_x4_k3x3_s1_w12_r152";
+    if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_ssr_o3_y7_x4_k3x3_s1_w12_r152";
     else if (Ho >= 20) prefs[0] = "sconv_tile_sbr_o3_y7_x4_k3x3_s1_w12_r152";
     else if (Ho >= 14) prefs[0] = "sconv_tile_o4_y4_x4_k3x3_s1_p2_w8_r232";
     else if (density < 0.2) prefs[0] = "sconv_tile_sbr_o4_y4_x4_k3x3_s1_w12_r152";
@@ -169,7 +169,7 @@ int tile_bwdw_variant(const escort_plan *plan) {
   const double density = (double)plan->nnz / ((double)g.num_output * (g.channels / g.group) * g.kernel_h * g.kernel_w);
   const char *pref = nullptr;
   if (k == 3 && g.kernel_w == 3) {
-    if (plan->Ho >= 14) pref = tma_w ? "sconv_tile_wa_o3_y7_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o3_y7_x4_k3x3_s1_w12_r152";
+    if (plan->Ho >= 14) pref = tma_w ? "sconv_tile_ws_o3_y7_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o3_y7_x4_k3x3_s1_w12_r152";
     else pref = density < 0.2 ? "sconv_tile_wb_o4_y4_x4_k3x3_s1_w12_r152" : "sconv_tile_wb_o5_y4_x4_k3x3_s1_w12_r152";
   } else if (k == 5 && g.kernel_w == 5) {
     pref = "sconv_tile_wb_o2_y4_x4_k5x5_s1_w12_r152";
@@ -293,6 +293,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   std::vector<Layout> cands;  // one per (WP, BR), best pitch / residue / lane order each
   for (int WP = 1; WP <= NCW; ++WP) {
     if (NCW % WP) continue;
+    if (V.SHFL && WP != 1) continue;  // halo shuffles: a tile row's lanes must be consecutive lanes of one warp
     const int lanes = WP * 32;
     const int WO = NCW / WP;
     for (int nb = 1; nb <= PY; ++nb) {
@@ -312,7 +313,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
       // pitch / skew / lane order with the fewest LDS.128 wavefronts
       int bP = Pmin, bskew = 0, border = 0, bcost = 1 << 30;
       const int orders[4] = {0, 4, 2, 1};
-      for (int oi = 0; oi < 4; ++oi) {
+      for (int oi = 0; oi < (V.SHFL ? 1 : 4); ++oi) {
         const std::vector<Slot> slots = enumerate_slots(GP, BR, PX, orders[oi]);
         for (int P = Pmin; P <= Pmin + 8 * per_vec; P += per_vec) {
           for (int skew = 0; skew <= (use_tma ? 0 : 28); skew += 4) {
@@ -620,8 +621,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     const std::vector<Slot> slots = enumerate_slots(GP, BR, PX, best.order);
     for (int i = 0; i < nslots; ++i) {
       const Slot &sl = slots[i];
-      lanes[i] = make_int4((sl.gs * slot_f + (sl.pyb * TY * S * P + lane_col0 + sl.px * TX * S) * PAIR) * 4, sl.gs, sl.pyb,
-                           sl.px);
+      const unsigned edge = (sl.px == 0 ? 1u : 0u) | (sl.px == PX - 1 ? 2u : 0u);
+      lanes[i] = make_int4((int)((unsigned)((sl.gs * slot_f + (sl.pyb * TY * S * P + lane_col0 + sl.px * TX * S) * PAIR) * 4) | (edge << 30)),
+                           sl.gs, sl.pyb, sl.px);
     }
   }
   int rc = 0;

@@ -261,7 +261,9 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
   // (kept deliberately lean: everything that is live across the interpreter block costs a register on top of the
   // accumulators, so unit coordinates and the lane record are recomputed in the epilogue instead of kept)
   if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
-  const unsigned lane_base_off = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+  // lane word: byte offset of the lane's patch in a stage | bit 30: first tile of its row | bit 31: last tile of its row
+  const unsigned lane_word = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+  const unsigned lane_base_off = lane_word & 0x3fffffffu, lane_edge = lane_word >> 30;
   const unsigned pitch_bytes = (unsigned)p.P * 4u * PAIR;
   float acc[IP::NACC];
   unsigned s = 0, ph = 0;
@@ -280,7 +282,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         const unsigned region = stage + p.in_bytes;
         unsigned seg;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(seg) : "r"(region + ow4));
-        IP::run(acc, region + seg, stage + lane_base_off, pitch_bytes, (unsigned)p.use_tma);
+        IP::run(acc, region + seg, stage + lane_base_off, pitch_bytes, lane_edge);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(empty_bar + 8 * s);
@@ -365,7 +367,8 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
       return;
     }
     if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
-    const unsigned lane_base_off = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+    const unsigned lane_word = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
+    const unsigned lane_base_off = lane_word & 0x3fffffffu, lane_edge = lane_word >> 30;
     const unsigned pitch_bytes = (unsigned)p.P * 4u;
     float *scratch = reinterpret_cast<float *>(smem_raw + p.scratch_off) + (size_t)wid * p.scratch_rows * 32;
     const unsigned scratch_lane = smem_base + p.scratch_off + ((unsigned)wid * p.scratch_rows * 32 + lane) * 4u;
@@ -405,7 +408,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
         unsigned seg, tapbase;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(seg) : "r"(region + ow4));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tapbase) : "r"(region + 4u * (unsigned)p.WO + ow4));
-        const unsigned ntaps = IP::run_w(dy, region + seg, stage + lane_base_off, pitch_bytes, scratch_lane);
+        const unsigned ntaps = IP::run_w(dy, region + seg, stage + lane_base_off, pitch_bytes, scratch_lane, lane_edge);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty_bar + 8 * s);  // the stage is no longer read: the sums live in the scratch rows
         for (unsigned k = lane; k < ntaps; k += 32) {

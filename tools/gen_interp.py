@@ -68,6 +68,8 @@ SIEVE_R = [
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", 1),
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "s", 1),   # TMA rows, halo columns by warp shuffle
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "s", 1),
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (5, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 512 channels / 5 -> 9 channel-block groups: 288 units = 2 full waves of 148
@@ -106,6 +108,51 @@ def load_plans(PC, PAIR, KW):
     return loads, loads_a, pos, PADL
 
 
+def emit_patch_loads(a, PLAN, PR, XW, TX, PADL, loads, loads_a, edge_operand=None):
+    """Patch rows -> registers.  PLAN "a": aligned body + scalar halo loads (TMA rows); "b": patch aligned (cp.async rows);
+    "s": TMA rows, but the halo columns come from the neighbouring lanes' bodies by warp shuffle (a 4-byte load with a
+    16-byte lane stride is a 4-way bank conflict: 12 LSU wavefronts per row against 4 + 2 here); the lanes of a tile
+    row are consecutive, the row's first / last lane (edge bits of the lane word) takes the image's zero padding."""
+    if PLAN != "s":
+        plan = loads_a if PLAN == "a" else loads
+        for r in range(PR):
+            for (po, cnt, byte) in plan:
+                b = r * XW + po
+                sgn = "+%d" % byte
+                if cnt == 4:
+                    a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
+                elif cnt == 2:
+                    a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
+                else:
+                    a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+        return
+    assert TX % 4 == 0 and PADL <= TX
+    for r in range(PR):
+        for q in range(TX // 4):
+            b = r * XW + PADL + 4 * q
+            a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d+%d];" % (b, b + 1, b + 2, b + 3, r, 16 * q))
+    for r in range(PR):
+        for j in range(PADL):
+            a("mov.b32 hb, x%d;" % (r * XW + TX + j))                 # neighbour's body column TX-PADL+j
+            a("shfl.sync.up.b32 hb, hb, 1, 0, 0xffffffff;")
+            a("mov.b32 hf, hb;")
+            a("selp.f32 x%d, 0f00000000, hf, pel;" % (r * XW + j))
+            a("mov.b32 hb, x%d;" % (r * XW + PADL + j))               # neighbour's body column j
+            a("shfl.sync.down.b32 hb, hb, 1, 0x1f, 0xffffffff;")
+            a("mov.b32 hf, hb;")
+            a("selp.f32 x%d, 0f00000000, hf, per;" % (r * XW + PADL + TX + j))
+
+
+def emit_edge_preds(a, operand):
+    a(".reg .pred pel, per;")
+    a(".reg .b32 hb, eb;")
+    a(".reg .f32 hf;")
+    a("and.b32 eb, %%%d, 1;" % operand)
+    a("setp.ne.u32 pel, eb, 0;")
+    a("and.b32 eb, %%%d, 2;" % operand)
+    a("setp.ne.u32 per, eb, 0;")
+
+
 def sieve_layout(OT, KH, KW):
     """bit position of handler (o, kh, kw): whole output channels per 32-bit mask word"""
     OPW = max(1, 32 // (KH * KW))
@@ -131,6 +178,8 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
     a(".reg .f32 x<%d>, w, wn, wn2;" % NX)
     a(".reg .b32 pc, pw, off, noff, t, t2, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
     a(".reg .pred p, pr<3>, pt<%d>;" % KW)
+    if PLAN == "s":
+        emit_edge_preds(a, NOPS + 3)
     # Stream (4-byte words): H_0 | H_1 W_0.. | H_2 W_1.. | ... | H_END W_(n-1).. ; H = {plane byte offset, masks};
     # the header of step i+1 precedes the weights of step i, so it is fetched a whole step ahead.
     # pc walks the headers and stays provably warp-uniform (advanced by the popcount of the masks), so the masks end
@@ -187,17 +236,7 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
     a("add.u32 ad0, %%%d, off;" % (NOPS + 1))
     for r in range(1, PR):
         a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, NOPS + 2))
-    plan = loads_a if PLAN == "a" else loads
-    for r in range(PR):
-        for (po, cnt, byte) in plan:
-            b = r * XW + po
-            sgn = "+%d" % byte
-            if cnt == 4:
-                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
-            elif cnt == 2:
-                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
-            else:
-                a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+    emit_patch_loads(a, PLAN, PR, XW, TX, PADL, loads, loads_a)
 
     def emit_taps(o, kh, single_test_done):
         wd, ob = o // OPW, (o % OPW) * KH * KW
@@ -262,14 +301,14 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
                % (OT, TY, TX, KH, KW, S, PAIR))
     src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;" % (NOPS, NC, PR, PC, XW, PADL))
     NTW = NCW + (4 if CREGS else NLW)
-    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;" % (NCW, NLW, NTW, CREGS, 1 if PLAN == "a" else 2))
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d, SHFL = %d;" % (NCW, NLW, NTW, CREGS, 2 if PLAN == "b" else 1, 1 if PLAN == "s" else 0))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
-    src.append("                                             unsigned pitch_bytes, unsigned /*plan_a*/) {")
+    src.append("                                             unsigned pitch_bytes, unsigned edge) {")
     src.append("    asm volatile(")
     src.append(body)
     src.append("      : %s" % ops_out)
-    src.append('      : "r"(prog), "r"(lane_base), "r"(pitch_bytes)')
+    src.append('      : "r"(prog), "r"(lane_base), "r"(pitch_bytes), "r"(edge)')
     src.append('      : "memory");')
     src.append("  }")
     src.append("};")
@@ -283,6 +322,8 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
 # weight gradient (one atomic per tap, unit and chunk).  Weights in the stream are skipped (pc advances by popcount).
 # tuple: (OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN)
 BWDW = [
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "s"),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "s"),
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "a"),
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b"),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a"),
@@ -315,6 +356,8 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
     a(".reg .f32 x<%d>, s<4>, r<2>;" % NX)
     a(".reg .b32 pc, pp, off, noff, t, t2, ad<%d>, m<%d>, nm<%d>;" % (PR, NW, NW))
     a(".reg .pred p, pr<3>, pt<%d>;" % KW)
+    if PLAN == "s":
+        emit_edge_preds(a, 1 + NOPS + 4)
     # operands: %0 = taps executed (out), %1.. = dy tile, then prog, lane_base, pitch_bytes, scratch (lane's column)
     I0 = 1
     a("mov.u32 pc, %%%d;" % (I0 + NOPS))
@@ -361,17 +404,7 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
     a("add.u32 ad0, %%%d, off;" % (I0 + NOPS + 1))
     for r in range(1, PR):
         a("add.u32 ad%d, ad%d, %%%d;" % (r, r - 1, I0 + NOPS + 2))
-    plan = loads_a if PLAN == "a" else loads
-    for r in range(PR):
-        for (po, cnt, byte) in plan:
-            b = r * XW + po
-            sgn = "+%d" % byte
-            if cnt == 4:
-                a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d%s];" % (b, b + 1, b + 2, b + 3, r, sgn))
-            elif cnt == 2:
-                a("ld.shared.v2.f32 {x%d, x%d}, [ad%d%s];" % (b, b + 1, r, sgn))
-            else:
-                a("ld.shared.f32 x%d, [ad%d%s];" % (b, r, sgn))
+    emit_patch_loads(a, PLAN, PR, XW, TX, PADL, loads, loads_a)
     for r in range(NR):
         o, kh = r // KH, r % KH
         wd, ob = o // OPW, (o % OPW) * KH * KW
@@ -427,17 +460,17 @@ def gen_bwdw(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN):
                % (OT, TY, TX, KH, KW, S, PAIR))
     src.append("  static constexpr int NACC = %d, NC = %d, PR = %d, PC = %d, XW = %d, PADL = %d;" % (NOPS, NC, PR, PC, XW, PADL))
     NTW = NCW + (4 if CREGS else NLW)
-    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;" % (NCW, NLW, NTW, CREGS, 5 if PLAN == "a" else 6))
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d, SHFL = %d;" % (NCW, NLW, NTW, CREGS, 6 if PLAN == "b" else 5, 1 if PLAN == "s" else 0))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  // returns the number of taps executed; their partials are in scratch rows 1 .. ntaps (row 0 is a dummy)")
     src.append("  __device__ __forceinline__ static unsigned run_w(const float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
-    src.append("                                                   unsigned pitch_bytes, unsigned scratch) {")
+    src.append("                                                   unsigned pitch_bytes, unsigned scratch, unsigned edge) {")
     src.append("    unsigned ntaps;")
     src.append("    asm volatile(")
     src.append(body)
     src.append('      : "=r"(ntaps)')
     src.append("      : %s," % ops_in)
-    src.append('        "r"(prog), "r"(lane_base), "r"(pitch_bytes), "r"(scratch)')
+    src.append('        "r"(prog), "r"(lane_base), "r"(pitch_bytes), "r"(scratch), "r"(edge)')
     src.append('      : "memory");')
     src.append("    return ntaps;")
     src.append("  }")
@@ -611,6 +644,7 @@ def gen_rows(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS, PLAN, TAP):
     NTW = NCW + (4 if CREGS else NLW)
     src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = %d;"
                % (NCW, NLW, NTW, CREGS, 3 if PLAN == "a" else 4))
+    src[-1] = src[-1].replace(";", ", SHFL = 0;", 1) if "SHFL" not in src[-1] else src[-1]
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base," % NOPS)
     src.append("                                             unsigned pitch_bytes, unsigned /*plan_a*/) {")
@@ -741,7 +775,7 @@ def gen_variant(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0):
     # CREGS > 0: the loader warps form a warpgroup of their own (4 warps, NLW of them active) that gives its
     # registers back with setmaxnreg.dec and the compute warpgroups grow to CREGS with setmaxnreg.inc
     NTW = NCW + (4 if CREGS else NLW)
-    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = 0;" % (NCW, NLW, NTW, CREGS))
+    src.append("  static constexpr int NCW = %d, NLW = %d, NTW = %d, CREGS = %d, MODE = 0, SHFL = 0;" % (NCW, NLW, NTW, CREGS))
     src.append('  static constexpr const char *name() { return "sconv_tile_%s"; }' % name)
     src.append("  __device__ __forceinline__ static void run(float (&acc)[%d], unsigned prog, unsigned lane_base,"
                % NOPS)
@@ -765,8 +799,8 @@ def main():
             "#pragma once",
             "template <int VID> struct Interp;"]
     ALL = ([(v, 0) for v in VARIANTS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE] +
-           [(v, 3 if v[10] == "a" else 4) for v in ROWS] + [(v, 1 if v[10] == "a" else 2) for v in SIEVE_R] +
-           [(v, 5 if v[10] == "a" else 6) for v in BWDW])
+           [(v, 3 if v[10] == "a" else 4) for v in ROWS] + [(v, 2 if v[10] == "b" else 1) for v in SIEVE_R] +
+           [(v, 6 if v[10] == "b" else 5) for v in BWDW])
     for i, (v, mode) in enumerate(ALL):
         path = os.path.join(OUTDIR, "interp_v%d.inc" % i)
         txt = "\n".join(head + [(gen_variant, gen_sieve, gen_sieve, gen_rows, gen_rows, gen_bwdw, gen_bwdw)[mode](i, *v)]) + "\n"
@@ -777,7 +811,8 @@ def main():
     def row(i, v, mode):
         cregs = v[9] if len(v) > 9 else 0
         ntw = v[7] + (4 if cregs else v[8])
-        return "  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + tuple(v[:9]) + (ntw, mode))
+        shfl = 1 if (len(v) > 10 and v[10] == "s") else 0
+        return "  X(%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d)" % ((i,) + tuple(v[:9]) + (ntw, mode, shfl))
     txt += " \\\n".join(row(i, v, mode) for i, (v, mode) in enumerate(ALL)) + "\n"
     if not os.path.exists(lst) or open(lst).read() != txt:
         open(lst, "w").write(txt)

@@ -131,7 +131,7 @@ static int choose_variant(const escort_geom &g, double density, int Ho) {
   const bool tma_w = g.width % 4 == 0 && g.pad_w == (k - 1) / 2 && tma_encoder() != nullptr && !getenv("ESCORT_NO_TMA");
   const char *prefs[4] = {nullptr, nullptr, nullptr, nullptr};
   if (k == 3 && g.kernel_w == 3 && s == 1) {
-    if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_ssr_o3_y7_x4_k3x3_s1_w12_r152";
+    if (tma_w && Ho >= 14) prefs[0] = "sconv_tile_ssr1_o3_y7_x4_k3x3_s1_w12_r152";
     else if (Ho >= 20) prefs[0] = "sconv_tile_sbr_o3_y7_x4_k3x3_s1_w12_r152";
     else if (Ho >= 14) prefs[0] = "sconv_tile_o4_y4_x4_k3x3_s1_p2_w8_r232";
     else if (density < 0.2) prefs[0] = "sconv_tile_sbr_o4_y4_x4_k3x3_s1_w12_r152";

@@ -68,8 +68,9 @@ SIEVE_R = [
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "a", 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "b", 1),
-    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "s", 1),   # TMA rows, halo columns by warp shuffle
-    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "s", 1),
+    # TMA rows, halo columns by warp shuffle; weights prefetched one tap ahead (one MOV less per tap, +1.5 % here)
+    (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "s", 1, 1),
+    (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "s", 1, 1),
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (5, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 512 channels / 5 -> 9 channel-block groups: 288 units = 2 full waves of 148
@@ -160,7 +161,7 @@ def sieve_layout(OT, KH, KW):
     return OPW, NW
 
 
-def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROLL=0):
+def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROLL=0, PF=2):
     assert PAIR == 1
     NACC = OT * TY * TX
     PR = (TY - 1) * S + KH
@@ -205,7 +206,8 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
     for k in range(NW):
         a("ld.shared.b32 nm%d, [pc+%d];" % (k, 4 + 4 * k))
     a("ld.shared.f32 wn, [pw+%d];" % HB)
-    a("ld.shared.f32 wn2, [pw+%d];" % (HB + 4))
+    if PF == 2:
+        a("ld.shared.f32 wn2, [pw+%d];" % (HB + 4))
     a("add.u32 pw, pw, %d;" % HB)      # pw -> the weight held in wn
     # pc -> header of step i+2 = past this step's weights
     a("popc.b32 t, m0;")
@@ -249,8 +251,11 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
             if not single_test_done:
                 a("@!pt%d bra.uni SH%dE;" % (kw, c))
             a("mov.f32 w, wn;")
-            a("mov.f32 wn, wn2;")
-            a("ld.shared.f32 wn2, [pw+8];")
+            if PF == 2:
+                a("mov.f32 wn, wn2;")
+                a("ld.shared.f32 wn2, [pw+8];")
+            else:
+                a("ld.shared.f32 wn, [pw+4];")
             a("add.u32 pw, pw, 4;")
             for ty in range(TY):
                 for tx in range(TX):
@@ -291,7 +296,7 @@ def gen_sieve(vid, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, CREGS=0, PLAN="b", ROL
     a("}")
     body = "\n".join('      "%s\\n\\t"' % s for s in L)
     ops_out = ", ".join('"+f"(acc[%d])' % i for i in range(NOPS))
-    name = "s%s%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, "r" if ROLL else "", OT, TY, TX, KH, KW, S, NCW,
+    name = "s%s%s%s_o%d_y%d_x%d_k%dx%d_s%d_w%d%s" % (PLAN, "r" if ROLL else "", "1" if PF == 1 else "", OT, TY, TX, KH, KW, S, NCW,
                                                   "_r%d" % CREGS if CREGS else "")
     src = []
     src.append("// ---- sieve variant %s: %d accumulator registers, %d patch registers, %d handlers, %d mask words ----"

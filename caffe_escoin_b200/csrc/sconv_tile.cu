@@ -301,7 +301,9 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
       if (nb > 1 && ceil_div(PY, nb - 1) == BR) continue;  // same BR as a smaller band count
       const int per_slot = BR * PX;
       if (per_slot > lanes) continue;
-      const int GP = std::min(lanes / per_slot, 16);
+      int GP = std::min(lanes / per_slot, 16);
+      if (V.SHFL && GP * per_slot >= 32) --GP;  // the shuffle-halo variants keep one lane spare (the zero lane)
+      if (GP < 1) continue;
       const int G = GP * PAIR;
       const int R = (BR * TY - 1) * S + KH;
       const int nslots = GP * per_slot;
@@ -622,9 +624,14 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
     for (int i = 0; i < nslots; ++i) {
       const Slot &sl = slots[i];
       const unsigned edge = (sl.px == 0 ? 1u : 0u) | (sl.px == PX - 1 ? 2u : 0u);
-      lanes[i] = make_int4((int)((unsigned)((sl.gs * slot_f + (sl.pyb * TY * S * P + lane_col0 + sl.px * TX * S) * PAIR) * 4) | (edge << 30)),
-                           sl.gs, sl.pyb, sl.px);
+      // shuffle-halo variants: the neighbours' lanes, or the spare lane `nslots` (parked on the zero halo block below)
+      // for the first / last tile of a row
+      const unsigned zl = (unsigned)(nslots & 31);
+      const unsigned srcl = sl.px == 0 ? zl : (unsigned)((i - 1) & 31), srcr = sl.px == PX - 1 ? zl : (unsigned)((i + 1) & 31);
+      const unsigned base = (unsigned)((sl.gs * slot_f + (sl.pyb * TY * S * P + lane_col0 + sl.px * TX * S) * PAIR) * 4);
+      lanes[i] = make_int4((int)(base | (srcl << 20) | (srcr << 25) | (edge << 30)), sl.gs, sl.pyb, sl.px);
     }
+    // lanes without a tile read the first 16 bytes of every row: the 4 halo columns TMA fills with zeros (offset 0)
   }
   int rc = 0;
   if ((rc = upload_vec(&tp->d_lanes, lanes, stream)) || (rc = upload_vec(&tp->d_oc_list, oc_list, stream)) ||

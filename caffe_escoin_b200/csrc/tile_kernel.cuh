@@ -261,9 +261,10 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
   // (kept deliberately lean: everything that is live across the interpreter block costs a register on top of the
   // accumulators, so unit coordinates and the lane record are recomputed in the epilogue instead of kept)
   if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
-  // lane word: byte offset of the lane's patch in a stage | bit 30: first tile of its row | bit 31: last tile of its row
+  // lane word: bits 0-19 byte offset of the lane's patch in a stage | 20-24 / 25-29 the lanes that hold its left / right
+  // neighbour tile (shuffle-halo variants) | 30 / 31 first / last tile of its row
   const unsigned lane_word = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
-  const unsigned lane_base_off = lane_word & 0x3fffffffu, lane_edge = lane_word >> 30;
+  const unsigned lane_base_off = lane_word & 0xfffffu, lane_edge = lane_word >> 20;
   const unsigned pitch_bytes = (unsigned)p.P * 4u * PAIR;
   float acc[IP::NACC];
   unsigned s = 0, ph = 0;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(Interp<VID>::NTW * 32, 1)
     }
     if constexpr (IP::CREGS > 0) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(IP::CREGS) : "memory");
     const unsigned lane_word = (unsigned)p.lanes[(wid % p.WP) * 32 + lane].x;
-    const unsigned lane_base_off = lane_word & 0x3fffffffu, lane_edge = lane_word >> 30;
+    const unsigned lane_base_off = lane_word & 0xfffffu, lane_edge = lane_word >> 20;
     const unsigned pitch_bytes = (unsigned)p.P * 4u;
     float *scratch = reinterpret_cast<float *>(smem_raw + p.scratch_off) + (size_t)wid * p.scratch_rows * 32;
     const unsigned scratch_lane = smem_base + p.scratch_off + ((unsigned)wid * p.scratch_rows * 32 + lane) * 4u;

@@ -72,6 +72,7 @@ SIEVE_R = [
     (3, 7, 4, 3, 3, 1, 1, 12, 4, 152, "s", 1, 1),
     (4, 7, 4, 3, 3, 1, 1, 8, 4, 232, "s", 1, 1),
     (4, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
+    (3, 4, 4, 3, 3, 1, 1, 16, 4, 104, "b", 1),   # four warps per scheduler; 384 channels = 8 exact groups of 16 x 3
     (6, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),
     (5, 4, 4, 3, 3, 1, 1, 12, 4, 152, "b", 1),   # 512 channels / 5 -> 9 channel-block groups: 288 units = 2 full waves of 148
     (4, 4, 4, 5, 5, 1, 1, 12, 4, 152, "b", 1),
@@ -113,7 +114,7 @@ def emit_patch_loads(a, PLAN, PR, XW, TX, PADL, loads, loads_a, edge_operand=Non
     """Patch rows -> registers.  PLAN "a": aligned body + scalar halo loads (TMA rows); "b": patch aligned (cp.async rows);
     "s": TMA rows, but the halo columns come from the neighbouring lanes' bodies by warp shuffle (a 4-byte load with a
     16-byte lane stride is a 4-way bank conflict: 12 LSU wavefronts per row against 4 + 2 here); the lanes of a tile
-    row are consecutive, the row's first / last lane (edge bits of the lane word) takes the image's zero padding."""
+    row are consecutive lanes of one warp."""
     if PLAN != "s":
         plan = loads_a if PLAN == "a" else loads
         for r in range(PR):
@@ -132,26 +133,24 @@ def emit_patch_loads(a, PLAN, PR, XW, TX, PADL, loads, loads_a, edge_operand=Non
         for q in range(TX // 4):
             b = r * XW + PADL + 4 * q
             a("ld.shared.v4.f32 {x%d, x%d, x%d, x%d}, [ad%d+%d];" % (b, b + 1, b + 2, b + 3, r, 16 * q))
+    # source lanes come with the lane word: the neighbours, or -- for the first / last tile of a row -- a spare lane
+    # parked on the row's TMA zero-filled halo block, so no select is needed
     for r in range(PR):
         for j in range(PADL):
-            a("mov.b32 hb, x%d;" % (r * XW + TX + j))                 # neighbour's body column TX-PADL+j
-            a("shfl.sync.up.b32 hb, hb, 1, 0, 0xffffffff;")
-            a("mov.b32 hf, hb;")
-            a("selp.f32 x%d, 0f00000000, hf, pel;" % (r * XW + j))
-            a("mov.b32 hb, x%d;" % (r * XW + PADL + j))               # neighbour's body column j
-            a("shfl.sync.down.b32 hb, hb, 1, 0x1f, 0xffffffff;")
-            a("mov.b32 hf, hb;")
-            a("selp.f32 x%d, 0f00000000, hf, per;" % (r * XW + PADL + TX + j))
+            a("mov.b32 hb, x%d;" % (r * XW + TX + j))                 # left neighbour's body column TX-PADL+j
+            a("shfl.sync.idx.b32 hb, hb, sl, 0x1f, 0xffffffff;")
+            a("mov.b32 x%d, hb;" % (r * XW + j))
+            a("mov.b32 hb, x%d;" % (r * XW + PADL + j))               # right neighbour's body column j
+            a("shfl.sync.idx.b32 hb, hb, sr, 0x1f, 0xffffffff;")
+            a("mov.b32 x%d, hb;" % (r * XW + PADL + TX + j))
 
 
 def emit_edge_preds(a, operand):
-    a(".reg .pred pel, per;")
-    a(".reg .b32 hb, eb;")
-    a(".reg .f32 hf;")
-    a("and.b32 eb, %%%d, 1;" % operand)
-    a("setp.ne.u32 pel, eb, 0;")
-    a("and.b32 eb, %%%d, 2;" % operand)
-    a("setp.ne.u32 per, eb, 0;")
+    """lane word >> 20: bits 0-4 = lane holding the left neighbour's body, bits 5-9 = the right neighbour's"""
+    a(".reg .b32 hb, sl, sr;")
+    a("and.b32 sl, %%%d, 31;" % operand)
+    a("shr.u32 sr, %%%d, 5;" % operand)
+    a("and.b32 sr, sr, 31;")
 
 
 def sieve_layout(OT, KH, KW):

@@ -302,7 +302,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
       const int per_slot = BR * PX;
       if (per_slot > lanes) continue;
       int GP = std::min(lanes / per_slot, 16);
-      if (V.SHFL && GP * per_slot >= 32) --GP;  // the shuffle-halo variants keep one lane spare (the zero lane)
+      if (V.SHFL && GP * per_slot >= 32) --GP;  // the TMA shuffle-halo variants keep one lane spare (the zero lane)
       if (GP < 1) continue;
       const int G = GP * PAIR;
       const int R = (BR * TY - 1) * S + KH;

@@ -57,3 +57,27 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")) or f == "Makefile":
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "escort_oracle" not in txt and "oracle/" not in txt, os.path.join(dp, f)
+
+
+def test_generated_variants_are_consistent():
+    """tools/gen_interp.py: one generated handler chain per variant, unique kernel names, and the variant table the
+    library was built from lists the same count (a stale generated/ directory would mis-number the variants)."""
+    import subprocess
+    import sys
+    gen = os.path.join(ROOT, "tools", "gen_interp.py")
+    n = int(subprocess.run([sys.executable, gen, "--count"], capture_output=True, text=True, check=True).stdout)
+    gdir = os.path.join(ROOT, "caffe_escoin_b200", "csrc", "generated")
+    lst = open(os.path.join(gdir, "variant_list.inc")).read()
+    assert "#define ESCORT_NUM_VARIANTS %d" % n in lst
+    names = []
+    for i in range(n):
+        txt = open(os.path.join(gdir, "interp_v%d.inc" % i)).read()
+        m = re.search(r'return "(sconv_tile_\w+)"', txt)
+        assert m, i
+        names.append(m.group(1))
+        assert "template <> struct Interp<%d>" % i in txt
+    assert len(set(names)) == n, [x for x in names if names.count(x) > 1]
+    # every default the planner names must exist
+    src = open(os.path.join(ROOT, "caffe_escoin_b200", "csrc", "sconv_tile.cu")).read()
+    for pref in set(re.findall(r'"(sconv_tile_\w+)"', src)):
+        assert pref in names, pref

@@ -42,6 +42,7 @@ struct Nz {
 };
 
 struct TilePlan;  // sconv_tile.cu
+struct TmemPlan;  // sconv_tmem.cu
 
 }  // namespace escort
 
@@ -67,6 +68,10 @@ struct escort_plan {
   int4 *d_wmeta;    // nnz (row-major order): {oc, ic, dy, dx}
   // ---- tile-interpreter forward (sconv_tile.cu) ----
   escort::TilePlan *tile;
+  // ---- TMEM-window forward (sconv_tmem.cu); at most one of tile / tm is set
+  escort::TmemPlan *tm;
+  int refreshed;        // escort_refresh_values has run: rebuilt streams re-gather their weights from d_meta
+  escort_plan *parent;  // backward-data sub-plan -> the layer's plan (owner of d_meta)
   std::vector<escort::Nz> *host_nz;  // kept for re-planning with another variant
   // ---- backward data through the tile kernel: dX = conv(dY, W^T flipped), a forward plan over the transposed,
   // 180-degree rotated weights (stride 1 only).  Built on first use; owns only g / nnz / host_nz / d_dense_idx / tile.
@@ -91,4 +96,18 @@ int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_
 const char *tile_kernel_name(const TilePlan *tp);
 int tile_num_variants();
 bool tile_variant_applies(const escort_plan *plan, int variant);  // variant = 1-based index
+int tile_regather(escort_plan *plan, const int4 *meta, cudaStream_t stream);
+// sconv_tmem.cu (variant ids follow the tile variants: tile_num_tile_variants() + 1 + tv)
+int tmem_num_variants();
+bool tmem_variant_applies(const escort_plan *plan, int tv);
+int tmem_choose_variant(const escort_plan *plan);
+int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream);
+void tmem_plan_free(TmemPlan *tp);
+bool tmem_batch_fits(const escort_plan *plan, int num);
+int tmem_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,
+                 cudaStream_t stream);
+int tmem_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream);
+int tmem_regather(escort_plan *plan, const int4 *meta, cudaStream_t stream);
+const char *tmem_kernel_name(const TmemPlan *tp);
+int tmem_describe(const TmemPlan *tp, char *buf, int buflen);
 }  // namespace escort

@@ -435,6 +435,7 @@ extern "C" int escort_plan_destroy(escort_plan *p) {
   cudaFree(p->d_tsrc);
   cudaFree(p->d_wmeta);
   if (p->tile) tile_plan_free(p->tile);
+  if (p->tm) tmem_plan_free(p->tm);
   if (p->tile_w) tile_plan_free(p->tile_w);
   if (p->bwd) escort_plan_destroy(p->bwd);
   delete p->host_nz;
@@ -488,9 +489,17 @@ static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
     cudaError_t e = cudaStreamSynchronize(stream);
     if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
   }
-  if (rc || !q->tile) {
+  if (rc || (!q->tile && !q->tm)) {
     escort_plan_destroy(q);
     return rc;
+  }
+  q->parent = p;
+  if (p->refreshed && p->d_meta) {
+    rc = tile_regather(q, p->d_meta, stream);
+    if (rc) {
+      escort_plan_destroy(q);
+      return rc;
+    }
   }
   p->bwd = q;
   return 0;
@@ -500,6 +509,7 @@ extern "C" long escort_plan_nnz(const escort_plan *p) { return p ? p->nnz : -1; 
 
 extern "C" const char *escort_plan_kernel_name(const escort_plan *p) {
   if (!p) return "null";
+  if (p->tm) return tmem_kernel_name(p->tm);
   if (p->tile) return tile_kernel_name(p->tile);
   return "sconv_fwd_generic";
 }
@@ -522,13 +532,24 @@ extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_ra
     tile_plan_free(p->tile);
     p->tile = nullptr;
   }
+  if (p->tm) {
+    tmem_plan_free(p->tm);
+    p->tm = nullptr;
+  }
   p->variant = variant;
   if (variant == 0) return 0;
   int rc = tile_plan_build(p, variant, 0);
   if (rc) return rc;
+  // a stream built after escort_refresh_values starts from the create-time snapshot (host_nz): re-gather the current
+  // values from the layer plan's device copy
+  const escort_plan *root = p->parent ? p->parent : p;
+  if (root->refreshed && root->d_meta && (p->tile || p->tm)) {
+    rc = tile_regather(p, root->d_meta, 0);
+    if (rc) return rc;
+  }
   ESCORT_CUDA(cudaStreamSynchronize(0));
-  if (variant > 0 && !p->tile) {
-    set_last_error("escort_plan_set_config: geometry / layout candidate not supported by the requested tile variant");
+  if (variant > 0 && !p->tile && !p->tm) {
+    set_last_error("escort_plan_set_config: geometry / layout candidate not supported by the requested variant");
     return ESCORT_EINVAL;
   }
   return 0;
@@ -556,7 +577,7 @@ static int autotune_one(escort_plan *p, int num, cudaStream_t stream) {
   cudaEventCreate(&e1);
   auto time_config = [&](int v, int rank) -> float {
     if (escort_plan_set_config(p, v, rank) != 0) return -1.f;  // no such layout candidate
-    if (v > 0 && !p->tile) return -1.f;
+    if (v > 0 && !p->tile && !p->tm) return -1.f;
     float ms_best = 1e30f;
     for (int it = 0; it < 3; ++it) {
       cudaEventRecord(e0, stream);
@@ -631,7 +652,9 @@ extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom
   ESCORT_REQUIRE(p && num >= 0, "escort_sconv_forward: bad arguments");
   if (num == 0) return 0;  // empty batch: nothing to do (pointers may be null)
   ESCORT_REQUIRE(bottom && top, "escort_sconv_forward: null tensor");
+  if (p->tm && tmem_batch_fits(p, num)) return tmem_forward(p, num, bottom, bias, fuse_relu, top, stream);
   if (p->tile) return tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
+  ESCORT_REQUIRE(p->d_rowptr, "escort_sconv_forward: batch too large for this plan");
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(p->Ho * p->Wo, kGenThreads), g.num_output, num);
   ESCORT_REQUIRE(num <= 65535, "escort_sconv_forward: batch too large for the generic kernel");
@@ -652,7 +675,8 @@ extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *
     int rc = build_bwd_plan(p, stream);
     if (rc) return rc;
   }
-  if (p->bwd && !getenv("ESCORT_GENERIC_BACKWARD")) return tile_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
+  if (p->bwd && !getenv("ESCORT_GENERIC_BACKWARD") && (p->bwd->tile || (p->bwd->tm && tmem_batch_fits(p->bwd, num))))
+    return escort_sconv_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
   sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
@@ -718,6 +742,8 @@ extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense,
     int rc = tile_refresh(p->bwd, weights_dense, stream);
     if (rc) return rc;
   }
-  if (p->tile) return tile_refresh(p, weights_dense, stream);
+  p->refreshed = 1;
+  p->refreshed = 1;
+  if (p->tile || p->tm) return tile_refresh(p, weights_dense, stream);
   return 0;
 }

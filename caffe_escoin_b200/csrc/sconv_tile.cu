@@ -107,9 +107,10 @@ void tile_plan_free(TilePlan *tp) {
 }
 
 const char *tile_kernel_name(const TilePlan *tp) { return tp->name; }
-int tile_num_variants() { return kNumVariants; }
+int tile_num_variants() { return kNumVariants + tmem_num_variants(); }
 bool tile_variant_applies(const escort_plan *plan, int variant) {
-  if (variant < 1 || variant > kNumVariants) return false;
+  if (variant > kNumVariants) return tmem_variant_applies(plan, variant - kNumVariants - 1);
+  if (variant < 1) return false;
   const VariantDesc &v = kVariants[variant - 1];
   const escort_geom &g = plan->g;
   return v.MODE < 5 && v.KH == g.kernel_h && v.KW == g.kernel_w && v.S == g.stride_h && g.stride_h == g.stride_w &&
@@ -197,6 +198,8 @@ static TmaEncodeFn tma_encoder() {
   return fn;
 }
 
+static thread_local bool g_building_w = false;
+
 namespace {
 struct Layout {
   int WP, G, BR, P, R, skew, order;
@@ -224,12 +227,20 @@ std::vector<Slot> enumerate_slots(int GP, int BR, int PX, int order) {
 }
 }  // namespace
 
-static thread_local bool g_building_w = false;
-
 int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   const int layout_rank = plan->layout_rank;
   plan->tile = nullptr;
+  plan->tm = nullptr;
   const escort_geom &g = plan->g;
+  // the TMEM-window kernel (sconv_tmem.cu): explicit variant ids above the tile variants, and the default wherever it applies
+  if (variant > kNumVariants) return layout_rank == 0 ? tmem_plan_build(plan, variant - kNumVariants - 1, stream) : 0;
+  if (variant <= 0 && !g_building_w) {
+    const int tv = tmem_choose_variant(plan);
+    if (tv >= 0) {
+      const int rc = tmem_plan_build(plan, tv, stream);
+      if (rc || plan->tm) return rc;
+    }
+  }
   if (g.dilation_h != 1 || g.dilation_w != 1 || g.stride_h != g.stride_w) return 0;
   if (g.width > 1024 || plan->nnz == 0) return 0;
   const int Cg = g.channels / g.group, Mg = g.num_output / g.group;
@@ -850,10 +861,26 @@ __global__ void tile_refresh_kernel(long nnz, const float *__restrict__ w_dense,
 }
 
 int tile_refresh(escort_plan *plan, const float *weights_dense, cudaStream_t stream) {
+  if (plan->tm) return tmem_refresh(plan, weights_dense, stream);
   TilePlan *tp = plan->tile;
   const unsigned blocks = (unsigned)((plan->nnz + 255) / 256);
   tile_refresh_kernel<<<blocks, 256, 0, stream>>>(plan->nnz, weights_dense, plan->d_dense_idx, tp->d_prog_pos,
                                                   reinterpret_cast<unsigned *>(tp->d_prog));
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void tile_regather_kernel(long nnz, const int4 *__restrict__ meta, const int *__restrict__ prog_pos,
+                                     unsigned *__restrict__ prog) {
+  const long j = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < nnz) prog[prog_pos[j]] = (unsigned)meta[j].w;
+}
+// weights of a freshly built stream from the plan's own value copy (d_meta[j].w, which escort_refresh_values keeps current)
+int tile_regather(escort_plan *plan, const int4 *meta, cudaStream_t stream) {
+  if (plan->tm) return tmem_regather(plan, meta, stream);
+  if (!plan->tile) return 0;
+  const unsigned blocks = (unsigned)((plan->nnz + 255) / 256);
+  tile_regather_kernel<<<blocks, 256, 0, stream>>>(plan->nnz, meta, plan->tile->d_prog_pos, reinterpret_cast<unsigned *>(plan->tile->d_prog));
   ESCORT_LAUNCH_CHECK();
   return 0;
 }
@@ -989,10 +1016,10 @@ static int describe_tile(const TilePlan *tp, char *buf, int buflen) {
 // " | bwd_data: <kernel + tiling>" and " | bwd_weight: <kernel + tiling>"
 extern "C" ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen) {
   if (!plan || !buf || buflen <= 0) return ESCORT_EINVAL;
-  int n = plan->tile ? describe_tile(plan->tile, buf, buflen) : snprintf(buf, buflen, "generic");
-  if (plan->bwd && plan->bwd->tile && n > 0 && n < buflen - 16) {
+  int n = plan->tm ? tmem_describe(plan->tm, buf, buflen) : plan->tile ? describe_tile(plan->tile, buf, buflen) : snprintf(buf, buflen, "generic");
+  if (plan->bwd && (plan->bwd->tile || plan->bwd->tm) && n > 0 && n < buflen - 16) {
     n += snprintf(buf + n, buflen - n, " | bwd_data: ");
-    if (n < buflen) n += describe_tile(plan->bwd->tile, buf + n, buflen - n);
+    if (n < buflen) n += plan->bwd->tm ? tmem_describe(plan->bwd->tm, buf + n, buflen - n) : describe_tile(plan->bwd->tile, buf + n, buflen - n);
   }
   if (plan->tile_w && n > 0 && n < buflen - 16) {
     n += snprintf(buf + n, buflen - n, " | bwd_weight: ");

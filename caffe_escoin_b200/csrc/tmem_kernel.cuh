@@ -1,0 +1,423 @@
+// tmem_kernel.cuh -- device side of the TMEM-window forward kernel (design notes: DESIGN.md section 4.4, host side:
+// sconv_tmem.cu).
+//
+// The reference walks one CSR row per output channel and reads the input through the "stretched" column index
+// (include/caffe/util/sconv.hpp:594-678, src/caffe/util/math_functions.cu:264-319): out[q] += w * in[q + off] over a
+// padded, flattened image.  Here the same walk runs with the input window resident in TENSOR MEMORY: a lane owns T
+// consecutive flattened output positions, its T + halo input floats of one channel sit in T + halo TMEM columns of its
+// own TMEM lane, and the shift of a nonzero (kh * pitch + kw) is the COLUMN ADDRESS of one tcgen05.ld -- an address,
+// not a register index, so there are no per-tap handlers, no masks and no patch registers.  Measured on B200
+// (tools/ubench/tmem_bench.cu): tcgen05.ld delivers 960 B/clk/SM against 128 B/clk/SM for shared memory, and the loop
+// "tcgen05.ld.x32 ; 16 x FFMA2" runs at 63 TFLOP/s (0.88 of the FP32 peak) at any weight density.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace escort {
+
+static constexpr int kTmMaxStages = 8;
+static constexpr int kTmMaxSlots = 16;
+// barrier area: smem_full[8] | smem_empty[8] | tm_full[4][16] | tm_empty[4][16] | tmem base slot
+static constexpr int kTmBarBytes = (2 * kTmMaxStages + 8 * kTmMaxSlots) * 8 + 128;
+
+struct TmParams {
+  // geometry
+  int C, H, W, M, Ho, Wo, pad_h, pad_w;
+  int Cg, Mg, ngroups;
+  int PW, IMGR, IMG;      // padded row pitch (W + pad_w), rows per image block (H + pad_h), positions per image block
+  int TILE, HALO, SW;     // flattened positions per work unit (32 * T), window halo, floats per staged channel row
+  int SLOTW, CHS, NSLOT;  // TMEM columns per channel window, channels per slot group, slot groups in the TMEM ring
+  int CI, nchunks, NS;    // channels per staged chunk, chunks per conv group, shared-memory stages
+  int nsg;                // slot groups per full chunk (CI / CHS)
+  int nblk, ogroups;      // channel blocks (OT channels each) per conv group, CTA passes (NCW blocks each) per conv group
+  int ntiles;             // filled per launch: ceil(num * IMG / TILE)
+  int stage0_off, stage_bytes, in_bytes, hdr_counts_off;
+  int ostage_off;         // per compute warp: TILE floats of output staging (transposes lane-major tiles for coalesced stores)
+  int rowtab_off, rowtab_stride;  // per producer warp: {src element offset | -1, dst position} per staged padded row
+  int lpr_shift, RO;      // loader: log2(lanes per padded row), rows per warp-wide copy instruction
+  const int *oc_list;     // [ngroups * nblk * OT] global output channel or -1
+  const uint4 *prog;      // record regions (16-byte units)
+  const int2 *rtab;       // [ngroups * ogroups * nchunks] {offset, length} of a region in 16-byte units
+  int *dbg;               // host-mapped debug words (bounded barrier waits report here before trapping), may be null
+};
+
+#ifndef ESCORT_TMEM_HOST_ONLY
+// ---- small PTX helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tm_mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tm_mbar_arrive(unsigned addr) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(addr) : "memory");
+}
+// Bounded wait: a protocol bug (or a lost arrival) must not hang the GPU.  After ~2 s without progress the first warp to
+// give up records {code, block, warp, barrier offset, parity} in the host-mapped debug words and traps.
+__device__ __forceinline__ void tm_mbar_wait(unsigned addr, unsigned parity, int code, int *dbg) {
+  unsigned ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok)
+               : "r"(addr), "r"(parity)
+               : "memory");
+  if (ok) return;
+  unsigned long long t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+    if (ok) return;
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 2000000000ull) {
+      if (dbg && (threadIdx.x & 31) == 0 && atomicCAS(dbg, 0, code) == 0) {
+        dbg[1] = (int)blockIdx.x;
+        dbg[2] = (int)(threadIdx.x >> 5);
+        dbg[3] = (int)(addr & 0xffffu);
+        dbg[4] = (int)parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tm_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// cp.async with zero fill: src_bytes = 0 writes zeros (halo positions and rows outside the batch)
+__device__ __forceinline__ void tm_cp_async4(unsigned dst_smem, const float *src, unsigned src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void tm_cp_async16(unsigned dst_smem, const void *src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+#define TM_O8(r, b) "=r"(r[b + 0]), "=r"(r[b + 1]), "=r"(r[b + 2]), "=r"(r[b + 3]), "=r"(r[b + 4]), "=r"(r[b + 5]), "=r"(r[b + 6]), "=r"(r[b + 7])
+#define TM_I8(r, b) "r"(r[b + 0]), "r"(r[b + 1]), "r"(r[b + 2]), "r"(r[b + 3]), "r"(r[b + 4]), "r"(r[b + 5]), "r"(r[b + 6]), "r"(r[b + 7])
+
+template <int T>
+__device__ __forceinline__ void tm_ld_window(uint32_t (&r)[T], uint32_t taddr);
+template <>
+__device__ __forceinline__ void tm_ld_window<32>(uint32_t (&r)[32], uint32_t taddr) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : TM_O8(r, 0), TM_O8(r, 8), TM_O8(r, 16), TM_O8(r, 24)
+      : "r"(taddr)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tm_ld_window<16>(uint32_t (&r)[16], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : TM_O8(r, 0), TM_O8(r, 8)
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+               TM_I8(r, 0), TM_I8(r, 8)
+               : "memory");
+}
+
+// 16-byte chunk swizzle of a staged channel row / an output staging tile: a lane's 128-bit accesses have a stride of
+// T/4 chunks, which alone would hit 2 (T = 16) or 1 (T = 32) of the 8 bank groups
+__device__ __forceinline__ unsigned tm_swz(unsigned chunk) { return chunk ^ ((chunk >> 3) & 7u); }
+
+struct TmUnit {
+  int og, cg, tile;
+};
+__device__ __forceinline__ TmUnit tm_decode_unit(const TmParams &p, int u) {
+  // og fastest: CTAs that share an input tile run at the same time and hit it in L2
+  TmUnit c;
+  c.og = u % p.ogroups; u /= p.ogroups;
+  c.cg = u % p.ngroups; u /= p.ngroups;
+  c.tile = u;
+  return c;
+}
+
+// ---- producer warps (one per TMEM lane quadrant): global -> shared (cp.async, zero-filled halo) -> TMEM windows -----
+template <int T, int NCW>
+__device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, const float *__restrict__ bottom, int nunits,
+                                                 unsigned char *smem_raw, unsigned smem_base, uint32_t tbase, int q, int lane) {
+  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
+  const unsigned tm_full = smem_base + 16 * kTmMaxStages + (unsigned)q * 8 * kTmMaxSlots;
+  const unsigned tm_empty = tm_full + 4 * 8 * kTmMaxSlots;
+  const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
+  int2 *rowtab = reinterpret_cast<int2 *>(smem_raw + p.rowtab_off + q * p.rowtab_stride);
+  const int my_units = blockIdx.x < (unsigned)nunits ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+  const int total = my_units * p.nchunks;
+  const int LA = p.NS - 2;  // chunks the loads run ahead of the fills (the stage being refilled was released a whole chunk ago, so a load never waits for the chunk the compute warps are on)
+  const size_t HW = (size_t)p.H * p.W;
+  int load_unit = -1, nrows = 0;
+  uint32_t g = 0;  // slot groups filled so far (TMEM ring position)
+  const int rsub = lane >> p.lpr_shift, xl = lane & ((1 << p.lpr_shift) - 1);
+
+  auto issue_load = [&](int it) {
+    const int ui = it / p.nchunks, c = it - ui * p.nchunks;
+    const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
+    const int s = it % p.NS;
+    if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
+    const long tile_start = (long)uc.tile * p.TILE;
+    if (ui != load_unit) {
+      // padded rows that intersect the staged range [tile_start, tile_start + SW)
+      load_unit = ui;
+      const long R0 = tile_start / p.PW;
+      nrows = (int)((tile_start + p.SW - 1) / p.PW - R0) + 1;
+      __syncwarp();
+      for (int j = lane; j < nrows; j += 32) {
+        const long R = R0 + j;
+        const int n = (int)(R / p.IMGR), yy = (int)(R - (long)n * p.IMGR);
+        const bool ok = n < num && yy >= p.pad_h;
+        rowtab[j] = make_int2(ok ? (int)(((size_t)n * p.C * p.H + (yy - p.pad_h)) * p.W) - p.pad_w : -1 - p.pad_w,
+                              (int)(R * p.PW - tile_start));
+      }
+      __syncwarp();
+    }
+    const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
+    const int cbase = uc.cg * p.Cg + c * p.CI;
+    const int nch = min(p.CI, p.Cg - c * p.CI);
+    for (int ch = q; ch < nch; ch += 4) {
+      const float *src_c = bottom + (size_t)(cbase + ch) * HW;
+      const unsigned row_addr = stage_addr + (unsigned)(ch * p.SW) * 4u;
+      for (int x = xl; x < p.PW; x += 32) {  // one trip unless the padded row is wider than 32
+#pragma unroll 4
+        for (int j = rsub; j < nrows; j += p.RO) {
+          const int2 e = rowtab[j];
+          const int d = e.y + x;
+          if (d >= 0 && d < p.SW) {
+            const bool data = e.x >= -p.pad_w && x >= p.pad_w;
+            const unsigned dst = row_addr + (tm_swz((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2);
+            tm_cp_async4(dst, data ? src_c + e.x + x : bottom, data ? 4u : 0u);
+          }
+        }
+      }
+    }
+    {  // record region of this (pass, chunk): contiguous 16-byte async copies
+      const int2 r = p.rtab[((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks + c];
+      const uint4 *src = p.prog + r.x;
+      const unsigned dst = stage_addr + p.in_bytes;
+      for (int i = q * 32 + lane; i < r.y; i += 128) tm_cp_async16(dst + 16u * i, src + i);
+    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
+  };
+
+  for (int it = 0; it < LA && it < total; ++it) issue_load(it);
+  for (int it = 0; it < total; ++it) {
+    if (it + LA < total) issue_load(it + LA);
+    const int s = it % p.NS;
+    tm_mbar_wait(smem_full + 8 * s, (unsigned)((it / p.NS) & 1), 2, p.dbg);
+    const int c = it % p.nchunks;
+    const int nch = min(p.CI, p.Cg - c * p.CI);
+    const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
+    for (int ch0 = 0; ch0 < nch; ch0 += p.CHS, ++g) {
+      const unsigned slot = g % (unsigned)p.NSLOT, round = g / (unsigned)p.NSLOT;
+      if (round > 0) {
+        tm_mbar_wait(tm_empty + 8 * slot, (round - 1) & 1u, 3, p.dbg);
+        tm_fence_after();
+      }
+      const int chn = min(p.CHS, nch - ch0);
+      for (int k = 0; k < chn; ++k) {
+        const unsigned row_addr = stage_addr + (unsigned)((ch0 + k) * p.SW) * 4u;
+        const uint32_t tcol = tq + slot * (unsigned)(p.CHS * p.SLOTW) + (unsigned)(k * p.SLOTW);
+#pragma unroll 2
+        for (int cb = 0; cb < p.SLOTW; cb += 16) {
+          uint32_t v[16];
+          const unsigned g0 = (unsigned)lane * (T / 4) + (unsigned)(cb >> 2);
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
+                         : "r"(row_addr + (tm_swz(g0 + j) << 4))
+                         : "memory");
+          tm_st16(tcol + cb, v);
+        }
+      }
+      tm_wait_st();
+      tm_fence_before();
+      __syncwarp();
+      if (lane == 0) tm_mbar_arrive(tm_full + 8 * slot);
+    }
+    __syncwarp();
+    if (lane == 0) tm_mbar_arrive(smem_empty + 8 * s);  // the producer's share; the compute warps still read the records
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------------------------
+// warps 0 .. NCW-1: compute (TMEM lane quadrant = wid % 4, channel block = wid); warps NCW .. NCW+3: producers.
+template <int T, int OT, int NCW, int CREGS, int PREGS>
+__global__ void __launch_bounds__((NCW + 4) * 32, 1)
+    sconv_tmem_kernel(const TmParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias, int fuse_relu,
+                      float *__restrict__ top, int nunits) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
+  const unsigned tm_full0 = smem_base + 16 * kTmMaxStages, tm_empty0 = tm_full0 + 4 * 8 * kTmMaxSlots;
+  uint32_t *tbase_slot = reinterpret_cast<uint32_t *>(smem_raw + (2 * kTmMaxStages + 8 * kTmMaxSlots) * 8);
+
+  if (tid == 0) {
+    for (int s = 0; s < p.NS; ++s) {
+      tm_mbar_init(smem_full + 8 * s, 128);        // every producer thread arrives through its cp.asyncs
+      tm_mbar_init(smem_empty + 8 * s, NCW + 4);   // every warp releases the stage
+    }
+    for (int qq = 0; qq < 4; ++qq)
+      for (int s = 0; s < p.NSLOT; ++s) {
+        tm_mbar_init(tm_full0 + (qq * kTmMaxSlots + s) * 8, 1);
+        tm_mbar_init(tm_empty0 + (qq * kTmMaxSlots + s) * 8, NCW / 4);
+      }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (wid == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"l"((uint64_t)__cvta_generic_to_shared(tbase_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tm_fence_before();
+  __syncthreads();
+  tm_fence_after();
+  const uint32_t tbase = *tbase_slot;
+
+  if (wid >= NCW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS) : "memory");
+    tm_producer_loop<T, NCW>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS) : "memory");
+    const int q = wid & 3;
+    const unsigned tm_full = tm_full0 + (unsigned)q * 8 * kTmMaxSlots, tm_empty = tm_empty0 + (unsigned)q * 8 * kTmMaxSlots;
+    const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
+    const unsigned slot_cols = (unsigned)(p.CHS * p.SLOTW);
+    unsigned long long acc[OT][T / 2];
+    unsigned st = 0, ph = 0;          // shared-memory stage ring
+    unsigned slot = 0, sph = 0;       // TMEM slot ring
+#pragma unroll 1
+    for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
+#pragma unroll
+      for (int o = 0; o < OT; ++o)
+#pragma unroll
+        for (int k = 0; k < T / 2; ++k) acc[o][k] = 0ull;
+#pragma unroll 1
+      for (int c = 0; c < p.nchunks; ++c) {
+        tm_mbar_wait(smem_full + 8 * st, ph, 4, p.dbg);
+        const unsigned region = smem_base + p.stage0_off + st * p.stage_bytes + p.in_bytes;
+        unsigned rp;  // this warp's records (8 bytes each: {TMEM column inside the slot group, fp32 weight})
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rp) : "r"(region + 4u * (unsigned)wid));
+        rp += region;
+        unsigned cp = region + p.hdr_counts_off + (unsigned)(wid * p.nsg) * 8u;  // per slot group: 8 tap counts (one byte per o)
+        const int nch = min(p.CI, p.Cg - c * p.CI);
+#pragma unroll 1
+        for (int ch0 = 0; ch0 < nch; ch0 += p.CHS) {
+          unsigned cnt_lo, cnt_hi;
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(cnt_lo), "=r"(cnt_hi) : "r"(cp));
+          cp += 8;
+          tm_mbar_wait(tm_full + 8 * slot, sph, 5, p.dbg);
+          tm_fence_after();
+          const uint32_t tslot = tq + slot * slot_cols;
+          if ((cnt_lo | cnt_hi) != 0u) {
+#pragma unroll
+            for (int o = 0; o < OT; ++o) {
+              unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
+#pragma unroll 1
+              for (; n > 0; --n) {
+                unsigned col, wbits;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
+                rp += 8;
+                uint32_t x[T];
+                tm_ld_window<T>(x, tslot + col);
+                unsigned long long w2;
+                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(w2) : "r"(wbits));
+                tm_wait_ld();
+#pragma unroll
+                for (int k = 0; k < T / 2; ++k) {
+                  unsigned long long xx;
+                  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(xx) : "r"(x[2 * k]), "r"(x[2 * k + 1]));
+                  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o][k]) : "l"(w2), "l"(xx));
+                }
+              }
+            }
+          }
+          tm_fence_before();
+          __syncwarp();
+          if (lane == 0) tm_mbar_arrive(tm_empty + 8 * slot);
+          if (++slot == (unsigned)p.NSLOT) {
+            slot = 0;
+            sph ^= 1u;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) tm_mbar_arrive(smem_empty + 8 * st);
+        if (++st == (unsigned)p.NS) {
+          st = 0;
+          ph ^= 1u;
+        }
+      }
+      // ---- epilogue: bias + ReLU, lane-major tile -> (swizzled) shared memory -> coalesced predicated stores ----
+      const TmUnit uc = tm_decode_unit(p, u);
+      const int blk = uc.og * NCW + wid;
+      if (blk < p.nblk) {
+        const int HoWo = p.Ho * p.Wo;
+        int ooff[T];  // where position i * 32 + lane of the tile goes (image offset + pixel), -1 = no such output
+        {
+          // (image, row, column) of the lane's first position by division, then 32 positions per step incrementally
+          const int pos = uc.tile * p.TILE + lane;  // the host checks num * IMG < 2^31
+          int n = pos / p.IMG;
+          const int r = pos - n * p.IMG;
+          int y = r / p.PW, x = r - y * p.PW;
+          const int dy = 32 / p.PW, dx = 32 - dy * p.PW;
+#pragma unroll
+          for (int i = 0; i < T; ++i) {
+            ooff[i] = (n < num && y < p.Ho && x < p.Wo) ? (n * p.M) * HoWo + y * p.Wo + x : -1;
+            x += dx;
+            y += dy;
+            if (x >= p.PW) {
+              x -= p.PW;
+              ++y;
+            }
+            while (y >= p.IMGR) {
+              y -= p.IMGR;
+              ++n;
+            }
+          }
+        }
+        const unsigned ost = smem_base + p.ostage_off + (unsigned)wid * (unsigned)(32 * T * 4);
+#pragma unroll
+        for (int o = 0; o < OT; ++o) {
+          const int oc = p.oc_list[((size_t)uc.cg * p.nblk + blk) * OT + o];
+          if (oc < 0) continue;
+          const float b = bias ? __ldg(bias + oc) : 0.f;
+#pragma unroll
+          for (int j = 0; j < T / 4; ++j) {
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              v[2 * e] = __uint_as_float((unsigned)(acc[o][2 * j + e] & 0xffffffffull)) + b;
+              v[2 * e + 1] = __uint_as_float((unsigned)(acc[o][2 * j + e] >> 32)) + b;
+            }
+            if (fuse_relu) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
+            }
+            const unsigned ch = tm_swz((unsigned)lane * (T / 4) + (unsigned)j);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ost + (ch << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+          }
+          __syncwarp();
+          float *out = top + (size_t)oc * HoWo;
+#pragma unroll
+          for (int i = 0; i < T; ++i) {
+            const unsigned pl = (unsigned)(i * 32 + lane);
+            float v;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ost + (tm_swz(pl >> 2) << 4) + ((pl & 3u) << 2)) : "memory");
+            if (ooff[i] >= 0) out[ooff[i]] = v;
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  tm_fence_before();
+  __syncthreads();
+  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+}
+#endif  // !ESCORT_TMEM_HOST_ONLY
+
+}  // namespace escort

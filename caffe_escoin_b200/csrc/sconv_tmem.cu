@@ -27,15 +27,16 @@ struct TmVariant {
   const void *kernel;
 };
 
-// (T, OT, NCW, compute registers, producer registers): (NCW * CREGS + 4 * PREGS) * 32 < 65536, with slack like the
-// tile kernel's setmaxnreg splits (an exact fit of the register file was never tried on hardware)
+// (T positions per lane, OT output channels per compute warp, NCW compute warps, compute / producer registers).  The
+// setmaxnreg split must stay inside the CTA's own register pool: NCW * (CREGS - R0) <= 4 * (R0 - PREGS) with R0 = the
+// launch allocation (static_assert in the kernel)
 #define ESCORT_TM_VARIANTS(X) \
-  X(16, 4, 16, 104, 56)       \
-  X(32, 2, 16, 104, 56)       \
-  X(16, 6, 12, 144, 56)       \
-  X(32, 3, 12, 144, 56)       \
-  X(16, 8, 8, 216, 56)        \
-  X(32, 4, 8, 216, 56)
+  X(16, 4, 16, 104, 64)       \
+  X(32, 2, 16, 104, 64)       \
+  X(16, 6, 12, 144, 72)       \
+  X(32, 3, 12, 144, 72)       \
+  X(16, 8, 8, 216, 72)        \
+  X(32, 4, 8, 216, 72)
 
 #define ESCORT_TM_ROW(T, OT, NCW, CR, PR) \
   {T, OT, NCW, CR, PR, "sconv_tmem_t" #T "_o" #OT "_w" #NCW, (const void *)&sconv_tmem_kernel<T, OT, NCW, CR, PR>},
@@ -153,11 +154,16 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   if (max_smem <= 0) max_smem = 227 * 1024;
   if (num_sms <= 0) num_sms = 148;
   const int nblk = ceil_div(Mg, OT), ogroups = ceil_div(nblk, NCW);
-  const int nrows_max = SW / PW + 3;
-  const int rowtab_stride = round_up(nrows_max * 8, 16);
+  // loader table: one {src, dst} entry per lane and copy step (RO padded rows, or one 32-column block of a wide row)
+  int lpr = 1, lpr_shift = 0;
+  while (lpr < PW && lpr < 32) { lpr <<= 1; ++lpr_shift; }
+  const int RO = 32 / lpr, nxb = (PW + 31) / 32;
+  const int ltab_n = ceil_div(SW / PW + 2, RO) * nxb;
+  const int ltab_bytes = round_up(ltab_n * 32 * 8, 128);
   const int stage0_off = round_up(kTmBarBytes, 1024);
-  const int ostage_bytes = NCW * TILE * 4;
-  const long budget = (long)max_smem - stage0_off - ostage_bytes - 4 * rowtab_stride - 1024;  // (1 KiB: base alignment slack)
+  const int SWP = SW / 32 * 36;                // staged row incl. skew padding (one pad chunk per 8 chunks)
+  const int ostage_bytes = NCW * (TILE / 32 * 36) * 4;
+  const long budget = (long)max_smem - stage0_off - ostage_bytes - ltab_bytes - 1024;  // (1 KiB: base alignment slack)
   if (budget <= 0) return 0;
 
   // ---- nnz-balanced channel blocks: rows sorted by nnz (descending), dealt in snake order ----
@@ -191,8 +197,10 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   int nchunks = 0, NS = 0, nsg = 0, in_bytes = 0, stage_bytes = 0, hdr_counts_off = 0;
   for (;;) {
     nchunks = ceil_div(Cg, CI);
+    CI = round_up(ceil_div(Cg, nchunks), CHS);  // even out the chunks (the fill lead D is bounded by the smallest one)
+    nchunks = ceil_div(Cg, CI);
     nsg = CI / CHS;
-    in_bytes = round_up(CI * SW * 4, 128);
+    in_bytes = round_up(CI * SWP * 4, 128);
     hdr_counts_off = round_up(NCW * 4, 16);
     const int hdr_bytes = round_up(hdr_counts_off + NCW * nsg * 8, 16);
     // bucket the nonzeros by (conv group, pass, chunk, warp)
@@ -263,15 +271,12 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   pr.nblk = nblk; pr.ogroups = ogroups;
   pr.stage0_off = stage0_off; pr.stage_bytes = stage_bytes; pr.in_bytes = in_bytes; pr.hdr_counts_off = hdr_counts_off;
   pr.ostage_off = stage0_off + NS * stage_bytes;
-  pr.rowtab_off = pr.ostage_off + ostage_bytes;
-  pr.rowtab_stride = rowtab_stride;
-  {
-    int lpr = 1, sh = 0;
-    while (lpr < PW && lpr < 32) { lpr <<= 1; ++sh; }
-    pr.lpr_shift = sh;
-    pr.RO = 32 / lpr;
-  }
-  tp->smem_bytes = (size_t)pr.rowtab_off + 4 * (size_t)rowtab_stride;
+  pr.ltab_off = pr.ostage_off + ostage_bytes;
+  pr.ltab_n = ltab_n;
+  pr.lpr_shift = lpr_shift;
+  pr.RO = RO;
+  pr.SWP = SWP;
+  tp->smem_bytes = (size_t)pr.ltab_off + (size_t)ltab_bytes;
   tp->nrecords = nz.size();
   std::vector<uint4> prog(words.size() / 4);
   memcpy(prog.data(), words.data(), words.size() * 4);

@@ -35,8 +35,9 @@ struct TmParams {
   int ntiles;             // filled per launch: ceil(num * IMG / TILE)
   int stage0_off, stage_bytes, in_bytes, hdr_counts_off;
   int ostage_off;         // per compute warp: TILE floats of output staging (transposes lane-major tiles for coalesced stores)
-  int rowtab_off, rowtab_stride;  // per producer warp: {src element offset | -1, dst position} per staged padded row
   int lpr_shift, RO;      // loader: log2(lanes per padded row), rows per warp-wide copy instruction
+  int ltab_off, ltab_n;   // loader table: smem offset, steps (entries = steps * 32 lanes)
+  int SWP;                // floats per staged channel row incl. the skew padding (SW / 32 * 36)
   const int *oc_list;     // [ngroups * nblk * OT] global output channel or -1
   const uint4 *prog;      // record regions (16-byte units)
   const int2 *rtab;       // [ngroups * ogroups * nchunks] {offset, length} of a region in 16-byte units
@@ -88,7 +89,7 @@ __device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 __device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // cp.async with zero fill: src_bytes = 0 writes zeros (halo positions and rows outside the batch)
 __device__ __forceinline__ void tm_cp_async4(unsigned dst_smem, const float *src, unsigned src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst_smem), "l"(src), "r"(src_bytes));
 }
 __device__ __forceinline__ void tm_cp_async16(unsigned dst_smem, const void *src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -120,9 +121,11 @@ __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&r)[16])
                : "memory");
 }
 
-// 16-byte chunk swizzle of a staged channel row / an output staging tile: a lane's 128-bit accesses have a stride of
-// T/4 chunks, which alone would hit 2 (T = 16) or 1 (T = 32) of the 8 bank groups
-__device__ __forceinline__ unsigned tm_swz(unsigned chunk) { return chunk ^ ((chunk >> 3) & 7u); }
+// Skew padding of a staged channel row / an output staging tile: one 16-byte pad chunk after every 8 chunks.  A lane's
+// 128-bit accesses have a stride of T/4 chunks, which alone would hit 2 (T = 16) or 1 (T = 32) of the 8 bank groups;
+// with the skew the 8 lanes of a quarter warp land on 8 different groups, and -- unlike an XOR swizzle -- the 4
+// chunks of an aligned 16-column block stay consecutive, so a fill block is one address + immediate offsets.
+__device__ __forceinline__ unsigned tm_skew(unsigned chunk) { return chunk + (chunk >> 3); }
 
 struct TmUnit {
   int og, cg, tile;
@@ -137,59 +140,71 @@ __device__ __forceinline__ TmUnit tm_decode_unit(const TmParams &p, int u) {
 }
 
 // ---- producer warps (one per TMEM lane quadrant): global -> shared (cp.async, zero-filled halo) -> TMEM windows -----
-template <int T, int NCW>
+template <int T, int NCW, int FB>
 __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, const float *__restrict__ bottom, int nunits,
                                                  unsigned char *smem_raw, unsigned smem_base, uint32_t tbase, int q, int lane) {
   const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
   const unsigned tm_full = smem_base + 16 * kTmMaxStages + (unsigned)q * 8 * kTmMaxSlots;
   const unsigned tm_empty = tm_full + 4 * 8 * kTmMaxSlots;
   const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
-  int2 *rowtab = reinterpret_cast<int2 *>(smem_raw + p.rowtab_off + q * p.rowtab_stride);
   const int my_units = blockIdx.x < (unsigned)nunits ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total = my_units * p.nchunks;
   const int LA = p.NS - 2;  // chunks the loads run ahead of the fills (the stage being refilled was released a whole chunk ago, so a load never waits for the chunk the compute warps are on)
-  const size_t HW = (size_t)p.H * p.W;
-  int load_unit = -1, nrows = 0;
+  const int HW = p.H * p.W;
+  int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
   uint32_t g = 0;  // slot groups filled so far (TMEM ring position)
-  const int rsub = lane >> p.lpr_shift, xl = lane & ((1 << p.lpr_shift) - 1);
+  int tab_unit = -1;
 
   auto issue_load = [&](int it) {
     const int ui = it / p.nchunks, c = it - ui * p.nchunks;
     const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
     const int s = it % p.NS;
-    if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
-    const long tile_start = (long)uc.tile * p.TILE;
-    if (ui != load_unit) {
-      // padded rows that intersect the staged range [tile_start, tile_start + SW)
-      load_unit = ui;
-      const long R0 = tile_start / p.PW;
-      nrows = (int)((tile_start + p.SW - 1) / p.PW - R0) + 1;
-      __syncwarp();
-      for (int j = lane; j < nrows; j += 32) {
-        const long R = R0 + j;
-        const int n = (int)(R / p.IMGR), yy = (int)(R - (long)n * p.IMGR);
-        const bool ok = n < num && yy >= p.pad_h;
-        rowtab[j] = make_int2(ok ? (int)(((size_t)n * p.C * p.H + (yy - p.pad_h)) * p.W) - p.pad_w : -1 - p.pad_w,
-                              (int)(R * p.PW - tile_start));
-      }
-      __syncwarp();
-    }
-    const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
-    const int cbase = uc.cg * p.Cg + c * p.CI;
-    const int nch = min(p.CI, p.Cg - c * p.CI);
-    for (int ch = q; ch < nch; ch += 4) {
-      const float *src_c = bottom + (size_t)(cbase + ch) * HW;
-      const unsigned row_addr = stage_addr + (unsigned)(ch * p.SW) * 4u;
-      for (int x = xl; x < p.PW; x += 32) {  // one trip unless the padded row is wider than 32
-#pragma unroll 4
-        for (int j = rsub; j < nrows; j += p.RO) {
-          const int2 e = rowtab[j];
-          const int d = e.y + x;
+    if (ui != tab_unit) {
+      // per-unit loader table, built by the four producer warps: entry (step j, lane) = {source element offset of the
+      // position inside channel 0's batch (-1: zero fill), skewed destination byte offset inside a staged channel
+      // row (-1: outside the staged range)}.  A step = RO padded rows x LPR columns (or one 32-column block of a wide row).
+      tab_unit = ui;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // every producer warp is done with the previous unit's table
+      const int tile_start = uc.tile * p.TILE;
+      const int R0 = tile_start / p.PW;
+      const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
+      const int nxb = (p.PW + 31) >> 5;
+      const int lpr = 1 << p.lpr_shift;
+      for (int e = q * 32 + lane; e < p.ltab_n * 32; e += 128) {
+        const int j = e >> 5, l = e & 31;
+        const int jr = j / nxb, xb = j - jr * nxb;
+        const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
+        int2 ent = make_int2(-1, -1);
+        if (row < nrows && x < p.PW) {
+          const int R = R0 + row;
+          const int d = R * p.PW + x - tile_start;
           if (d >= 0 && d < p.SW) {
-            const bool data = e.x >= -p.pad_w && x >= p.pad_w;
-            const unsigned dst = row_addr + (tm_swz((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2);
-            tm_cp_async4(dst, data ? src_c + e.x + x : bottom, data ? 4u : 0u);
+            const int n = R / p.IMGR, yy = R - n * p.IMGR;
+            ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
+            if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = (n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w);
           }
+        }
+        ltab[e] = ent;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
+    const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
+    const int nch = min(p.CI, p.Cg - c * p.CI);
+    const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
+    const unsigned row_bytes = (unsigned)p.SWP * 4u;
+    for (int j = q; j < p.ltab_n; j += 4) {  // this warp's table steps, all channels of the chunk
+      const int2 e = ltab[j * 32 + lane];
+      if (e.y >= 0) {
+        const float *src = e.x >= 0 ? src0 + e.x : bottom;
+        const unsigned nbytes = e.x >= 0 ? 4u : 0u;
+        const size_t sstep = e.x >= 0 ? (size_t)HW : 0;
+        unsigned dst = stage_addr + (unsigned)e.y;
+#pragma unroll 4
+        for (int ch = 0; ch < nch; ++ch) {
+          tm_cp_async4(dst, src, nbytes);
+          src += sstep;
+          dst += row_bytes;
         }
       }
     }
@@ -203,6 +218,8 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
   };
 
   for (int it = 0; it < LA && it < total; ++it) issue_load(it);
+  // lane's first chunk of a window (before the skew): lane * T/4; a 16-column block never straddles a pad chunk
+  const unsigned lane_chunk = (unsigned)lane * (T / 4);
   for (int it = 0; it < total; ++it) {
     if (it + LA < total) issue_load(it + LA);
     const int s = it % p.NS;
@@ -218,19 +235,25 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
       }
       const int chn = min(p.CHS, nch - ch0);
       for (int k = 0; k < chn; ++k) {
-        const unsigned row_addr = stage_addr + (unsigned)((ch0 + k) * p.SW) * 4u;
+        const unsigned row_addr = stage_addr + (unsigned)((ch0 + k) * p.SWP) * 4u;
         const uint32_t tcol = tq + slot * (unsigned)(p.CHS * p.SLOTW) + (unsigned)(k * p.SLOTW);
-#pragma unroll 2
-        for (int cb = 0; cb < p.SLOTW; cb += 16) {
-          uint32_t v[16];
-          const unsigned g0 = (unsigned)lane * (T / 4) + (unsigned)(cb >> 2);
+        for (int cb = 0; cb < p.SLOTW; cb += 16 * FB) {
+          // FB blocks of 16 window columns per round: all the 128-bit loads first, then the TMEM stores
+          uint32_t v[FB][16];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
-                         : "=r"(v[4 * j]), "=r"(v[4 * j + 1]), "=r"(v[4 * j + 2]), "=r"(v[4 * j + 3])
-                         : "r"(row_addr + (tm_swz(g0 + j) << 4))
-                         : "memory");
-          tm_st16(tcol + cb, v);
+          for (int b = 0; b < FB; ++b)
+            if (cb + 16 * b < p.SLOTW) {
+              const unsigned a = row_addr + (tm_skew(lane_chunk + (unsigned)((cb >> 2) + 4 * b)) << 4);
+#define TM_LDS128(J) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+" #J "*16];" : "=r"(v[b][4 * J]), "=r"(v[b][4 * J + 1]), "=r"(v[b][4 * J + 2]), "=r"(v[b][4 * J + 3]) : "r"(a))
+              TM_LDS128(0);
+              TM_LDS128(1);
+              TM_LDS128(2);
+              TM_LDS128(3);
+#undef TM_LDS128
+            }
+#pragma unroll
+          for (int b = 0; b < FB; ++b)
+            if (cb + 16 * b < p.SLOTW) tm_st16(tcol + cb + 16 * b, v[b]);
         }
       }
       tm_wait_st();
@@ -249,6 +272,11 @@ template <int T, int OT, int NCW, int CREGS, int PREGS>
 __global__ void __launch_bounds__((NCW + 4) * 32, 1)
     sconv_tmem_kernel(const TmParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias, int fuse_relu,
                       float *__restrict__ top, int nunits) {
+  // setmaxnreg moves registers inside the CTA's OWN pool (what the launch allocated: R0 per thread), not the whole
+  // register file: the compute warps can only grow by what the producer warps give back.  (Measured the hard way: a
+  // split that needed the SM's unallocated registers left the last compute warpgroup spinning in setmaxnreg.inc.)
+  constexpr int R0 = 65536 / ((NCW + 4) * 32) / 8 * 8;
+  static_assert(NCW * (CREGS - R0) <= 4 * (R0 - PREGS), "setmaxnreg split exceeds the CTA register pool");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -280,7 +308,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
 
   if (wid >= NCW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS) : "memory");
-    tm_producer_loop<T, NCW>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
+    tm_producer_loop<T, NCW, (PREGS >= 72 ? 3 : 2)>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS) : "memory");
     const int q = wid & 3;
@@ -303,6 +331,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
         unsigned rp;  // this warp's records (8 bytes each: {TMEM column inside the slot group, fp32 weight})
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rp) : "r"(region + 4u * (unsigned)wid));
         rp += region;
+        unsigned col, wbits;  // the NEXT record, always one tap ahead (its load overlaps the current tap's FMAs)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
         unsigned cp = region + p.hdr_counts_off + (unsigned)(wid * p.nsg) * 8u;  // per slot group: 8 tap counts (one byte per o)
         const int nch = min(p.CI, p.Cg - c * p.CI);
 #pragma unroll 1
@@ -319,13 +349,12 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
               unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
 #pragma unroll 1
               for (; n > 0; --n) {
-                unsigned col, wbits;
-                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
-                rp += 8;
                 uint32_t x[T];
                 tm_ld_window<T>(x, tslot + col);
                 unsigned long long w2;
                 asm volatile("mov.b64 %0, {%1, %1};" : "=l"(w2) : "r"(wbits));
+                rp += 8;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
                 tm_wait_ld();
 #pragma unroll
                 for (int k = 0; k < T / 2; ++k) {
@@ -379,7 +408,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
             }
           }
         }
-        const unsigned ost = smem_base + p.ostage_off + (unsigned)wid * (unsigned)(32 * T * 4);
+        const unsigned ost = smem_base + p.ostage_off + (unsigned)wid * (unsigned)(36 * T * 4);  // TILE floats + skew padding
 #pragma unroll
         for (int o = 0; o < OT; ++o) {
           const int oc = p.oc_list[((size_t)uc.cg * p.nblk + blk) * OT + o];
@@ -397,7 +426,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = fmaxf(v[e], 0.f);
             }
-            const unsigned ch = tm_swz((unsigned)lane * (T / 4) + (unsigned)j);
+            const unsigned ch = tm_skew((unsigned)lane * (T / 4) + (unsigned)j);
             asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(ost + (ch << 4)), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
           }
           __syncwarp();
@@ -406,7 +435,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
           for (int i = 0; i < T; ++i) {
             const unsigned pl = (unsigned)(i * 32 + lane);
             float v;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ost + (tm_swz(pl >> 2) << 4) + ((pl & 3u) << 2)) : "memory");
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ost + (tm_skew(pl >> 2) << 4) + ((pl & 3u) << 2)) : "memory");
             if (ooff[i] >= 0) out[ooff[i]] = v;
           }
           __syncwarp();

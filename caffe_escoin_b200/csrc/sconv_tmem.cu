@@ -22,24 +22,27 @@
 namespace escort {
 
 struct TmVariant {
-  int T, OT, NCW, CREGS, PREGS;
+  int T, OT, NCW, NPW, CREGS, PREGS;
   const char *name;
   const void *kernel;
 };
 
-// (T positions per lane, OT output channels per compute warp, NCW compute warps, compute / producer registers).  The
-// setmaxnreg split must stay inside the CTA's own register pool: NCW * (CREGS - R0) <= 4 * (R0 - PREGS) with R0 = the
-// launch allocation (static_assert in the kernel)
-#define ESCORT_TM_VARIANTS(X) \
-  X(16, 4, 16, 104, 64)       \
-  X(32, 2, 16, 104, 64)       \
-  X(16, 6, 12, 144, 72)       \
-  X(32, 3, 12, 144, 72)       \
-  X(16, 8, 8, 216, 72)        \
-  X(32, 4, 8, 216, 72)
+// (T positions per lane, OT output channels per compute warp, NCW compute warps, NPW producer warps, compute /
+// producer registers).  The setmaxnreg split must stay inside the CTA's own register pool:
+// NCW * (CREGS - R0) <= NPW * (R0 - PREGS) with R0 = the launch allocation (static_assert in the kernel)
+#define ESCORT_TM_VARIANTS(X)  \
+  X(16, 4, 16, 4, 104, 64)     \
+  X(32, 2, 16, 4, 104, 64)     \
+  X(16, 6, 12, 4, 144, 72)     \
+  X(32, 3, 12, 4, 144, 72)     \
+  X(16, 8, 8, 4, 216, 72)      \
+  X(32, 4, 8, 4, 216, 72)      \
+  X(16, 5, 12, 8, 128, 48)     \
+  X(16, 8, 8, 8, 192, 64)      \
+  X(32, 4, 8, 8, 192, 64)
 
-#define ESCORT_TM_ROW(T, OT, NCW, CR, PR) \
-  {T, OT, NCW, CR, PR, "sconv_tmem_t" #T "_o" #OT "_w" #NCW, (const void *)&sconv_tmem_kernel<T, OT, NCW, CR, PR>},
+#define ESCORT_TM_ROW(T, OT, NCW, NPW, CR, PR) \
+  {T, OT, NCW, NPW, CR, PR, "sconv_tmem_t" #T "_o" #OT "_w" #NCW "p" #NPW, (const void *)&sconv_tmem_kernel<T, OT, NCW, NPW, CR, PR>},
 static const TmVariant kTmVariants[] = {ESCORT_TM_VARIANTS(ESCORT_TM_ROW)};
 static constexpr int kNumTmVariants = (int)(sizeof(kTmVariants) / sizeof(kTmVariants[0]));
 
@@ -314,7 +317,7 @@ int tmem_forward(escort_plan *plan, int num, const float *bottom, const float *b
   const unsigned grid = (unsigned)std::min(nunits, tp->num_sms);
   const TmVariant &V = kTmVariants[tp->vidx];
   void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&bias, (void *)&fuse_relu, (void *)&top, (void *)&nunits};
-  ESCORT_CUDA(cudaLaunchKernel(V.kernel, dim3(grid), dim3((V.NCW + 4) * 32), args, tp->smem_bytes, stream));
+  ESCORT_CUDA(cudaLaunchKernel(V.kernel, dim3(grid), dim3((V.NCW + V.NPW) * 32), args, tp->smem_bytes, stream));
   return 0;
 }
 

@@ -115,6 +115,46 @@ __device__ __forceinline__ void tm_ld_window<16>(uint32_t (&r)[16], uint32_t tad
                : "r"(taddr)
                : "memory");
 }
+// One nonzero: tcgen05.ld of the lane's T-column window at `taddr`, then T/2 packed FMAs acc += {w, w} * x.  Kept as ONE
+// asm block so that ptxas sees the accumulators as plain in/out operands of the FMAs (as separate statements it
+// computed the FMAs into the window registers and copied all of them back: 16 extra MOVs per nonzero).
+template <int T>
+__device__ __forceinline__ void tm_tap(unsigned long long (&acc)[T / 2], uint32_t taddr, unsigned wbits);
+template <>
+__device__ __forceinline__ void tm_tap<16>(unsigned long long (&a)[8], uint32_t taddr, unsigned wbits) {
+  asm volatile(
+      "{\n\t.reg .b32 t<16>;\n\t.reg .b64 p<8>, w2;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
+      "mov.b64 w2, {%9, %9};\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 p0, {t0, t1};\n\tmov.b64 p1, {t2, t3};\n\tmov.b64 p2, {t4, t5};\n\tmov.b64 p3, {t6, t7};\n\t"
+      "mov.b64 p4, {t8, t9};\n\tmov.b64 p5, {t10, t11};\n\tmov.b64 p6, {t12, t13};\n\tmov.b64 p7, {t14, t15};\n\t"
+      "fma.rn.f32x2 %0, w2, p0, %0;\n\tfma.rn.f32x2 %1, w2, p1, %1;\n\tfma.rn.f32x2 %2, w2, p2, %2;\n\tfma.rn.f32x2 %3, w2, p3, %3;\n\t"
+      "fma.rn.f32x2 %4, w2, p4, %4;\n\tfma.rn.f32x2 %5, w2, p5, %5;\n\tfma.rn.f32x2 %6, w2, p6, %6;\n\tfma.rn.f32x2 %7, w2, p7, %7;\n\t}"
+      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7])
+      : "r"(taddr), "r"(wbits)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tm_tap<32>(unsigned long long (&a)[16], uint32_t taddr, unsigned wbits) {
+  asm volatile(
+      "{\n\t.reg .b32 t<32>;\n\t.reg .b64 p<16>, w2;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15,t16,t17,t18,t19,t20,t21,t22,t23,t24,t25,t26,t27,t28,t29,t30,t31}, [%16];\n\t"
+      "mov.b64 w2, {%17, %17};\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 p0, {t0, t1};\n\tmov.b64 p1, {t2, t3};\n\tmov.b64 p2, {t4, t5};\n\tmov.b64 p3, {t6, t7};\n\t"
+      "mov.b64 p4, {t8, t9};\n\tmov.b64 p5, {t10, t11};\n\tmov.b64 p6, {t12, t13};\n\tmov.b64 p7, {t14, t15};\n\t"
+      "mov.b64 p8, {t16, t17};\n\tmov.b64 p9, {t18, t19};\n\tmov.b64 p10, {t20, t21};\n\tmov.b64 p11, {t22, t23};\n\t"
+      "mov.b64 p12, {t24, t25};\n\tmov.b64 p13, {t26, t27};\n\tmov.b64 p14, {t28, t29};\n\tmov.b64 p15, {t30, t31};\n\t"
+      "fma.rn.f32x2 %0, w2, p0, %0;\n\tfma.rn.f32x2 %1, w2, p1, %1;\n\tfma.rn.f32x2 %2, w2, p2, %2;\n\tfma.rn.f32x2 %3, w2, p3, %3;\n\t"
+      "fma.rn.f32x2 %4, w2, p4, %4;\n\tfma.rn.f32x2 %5, w2, p5, %5;\n\tfma.rn.f32x2 %6, w2, p6, %6;\n\tfma.rn.f32x2 %7, w2, p7, %7;\n\t"
+      "fma.rn.f32x2 %8, w2, p8, %8;\n\tfma.rn.f32x2 %9, w2, p9, %9;\n\tfma.rn.f32x2 %10, w2, p10, %10;\n\tfma.rn.f32x2 %11, w2, p11, %11;\n\t"
+      "fma.rn.f32x2 %12, w2, p12, %12;\n\tfma.rn.f32x2 %13, w2, p13, %13;\n\tfma.rn.f32x2 %14, w2, p14, %14;\n\tfma.rn.f32x2 %15, w2, p15, %15;\n\t}"
+      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7]), "+l"(a[8]), "+l"(a[9]),
+        "+l"(a[10]), "+l"(a[11]), "+l"(a[12]), "+l"(a[13]), "+l"(a[14]), "+l"(a[15])
+      : "r"(taddr), "r"(wbits)
+      : "memory");
+}
 __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
                TM_I8(r, 0), TM_I8(r, 8)
@@ -140,9 +180,13 @@ __device__ __forceinline__ TmUnit tm_decode_unit(const TmParams &p, int u) {
 }
 
 // ---- producer warps (one per TMEM lane quadrant): global -> shared (cp.async, zero-filled halo) -> TMEM windows -----
-template <int T, int NCW, int FB>
+// NPW producer warps = NPW / 4 per quadrant; pw = producer warp index, quadrant = pw % 4, pa = pw / 4 = which share of a
+// slot group's 16-column blocks this warp fills.
+template <int T, int NCW, int NPW, int FB>
 __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, const float *__restrict__ bottom, int nunits,
-                                                 unsigned char *smem_raw, unsigned smem_base, uint32_t tbase, int q, int lane) {
+                                                 unsigned char *smem_raw, unsigned smem_base, uint32_t tbase, int pw, int lane) {
+  constexpr int NPQ = NPW / 4;
+  const int q = pw & 3, pa = pw >> 2;
   const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
   const unsigned tm_full = smem_base + 16 * kTmMaxStages + (unsigned)q * 8 * kTmMaxSlots;
   const unsigned tm_empty = tm_full + 4 * 8 * kTmMaxSlots;
@@ -152,7 +196,9 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
   const int LA = p.NS - 2;  // chunks the loads run ahead of the fills (the stage being refilled was released a whole chunk ago, so a load never waits for the chunk the compute warps are on)
   const int HW = p.H * p.W;
   int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
-  uint32_t g = 0;  // slot groups filled so far (TMEM ring position)
+  unsigned slot = 0, round = 0;  // TMEM ring position of the next slot group to fill
+  unsigned gsel = 0;             // slot groups seen so far (which producer of the quadrant fills the next one)
+  const int nblocks = p.SLOTW >> 4;  // 16-column blocks per channel window
   int tab_unit = -1;
 
   auto issue_load = [&](int it) {
@@ -164,13 +210,13 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
       // position inside channel 0's batch (-1: zero fill), skewed destination byte offset inside a staged channel
       // row (-1: outside the staged range)}.  A step = RO padded rows x LPR columns (or one 32-column block of a wide row).
       tab_unit = ui;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // every producer warp is done with the previous unit's table
+      asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");  // every producer warp is done with the previous unit's table
       const int tile_start = uc.tile * p.TILE;
       const int R0 = tile_start / p.PW;
       const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
       const int nxb = (p.PW + 31) >> 5;
       const int lpr = 1 << p.lpr_shift;
-      for (int e = q * 32 + lane; e < p.ltab_n * 32; e += 128) {
+      for (int e = pw * 32 + lane; e < p.ltab_n * 32; e += NPW * 32) {
         const int j = e >> 5, l = e & 31;
         const int jr = j / nxb, xb = j - jr * nxb;
         const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
@@ -186,14 +232,14 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
         }
         ltab[e] = ent;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
     }
     if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
     const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
     const int nch = min(p.CI, p.Cg - c * p.CI);
     const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
     const unsigned row_bytes = (unsigned)p.SWP * 4u;
-    for (int j = q; j < p.ltab_n; j += 4) {  // this warp's table steps, all channels of the chunk
+    for (int j = pw; j < p.ltab_n; j += NPW) {  // this warp's table steps, all channels of the chunk
       const int2 e = ltab[j * 32 + lane];
       if (e.y >= 0) {
         const float *src = e.x >= 0 ? src0 + e.x : bottom;
@@ -212,7 +258,7 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
       const int2 r = p.rtab[((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks + c];
       const uint4 *src = p.prog + r.x;
       const unsigned dst = stage_addr + p.in_bytes;
-      for (int i = q * 32 + lane; i < r.y; i += 128) tm_cp_async16(dst + 16u * i, src + i);
+      for (int i = pw * 32 + lane; i < r.y; i += NPW * 32) tm_cp_async16(dst + 16u * i, src + i);
     }
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
   };
@@ -227,39 +273,53 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
     const int c = it % p.nchunks;
     const int nch = min(p.CI, p.Cg - c * p.CI);
     const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
-    for (int ch0 = 0; ch0 < nch; ch0 += p.CHS, ++g) {
-      const unsigned slot = g % (unsigned)p.NSLOT, round = g / (unsigned)p.NSLOT;
+    for (int ch0 = 0; ch0 < nch; ch0 += p.CHS) {
+      if (NPQ > 1 && (int)(gsel++ & (NPQ - 1)) != pa) {  // the quadrant's producers take slot groups in turn
+        if (++slot == (unsigned)p.NSLOT) {
+          slot = 0;
+          ++round;
+        }
+        continue;
+      }
       if (round > 0) {
         tm_mbar_wait(tm_empty + 8 * slot, (round - 1) & 1u, 3, p.dbg);
         tm_fence_after();
       }
       const int chn = min(p.CHS, nch - ch0);
-      for (int k = 0; k < chn; ++k) {
-        const unsigned row_addr = stage_addr + (unsigned)((ch0 + k) * p.SWP) * 4u;
-        const uint32_t tcol = tq + slot * (unsigned)(p.CHS * p.SLOTW) + (unsigned)(k * p.SLOTW);
-        for (int cb = 0; cb < p.SLOTW; cb += 16 * FB) {
-          // FB blocks of 16 window columns per round: all the 128-bit loads first, then the TMEM stores
+      unsigned row_addr = stage_addr + (unsigned)(ch0 * p.SWP) * 4u;
+      uint32_t tcol = tq + slot * (unsigned)(p.CHS * p.SLOTW);
+      for (int k = 0; k < chn; ++k, row_addr += (unsigned)p.SWP * 4u, tcol += (unsigned)p.SLOTW) {
+        // the channel window in 16-column blocks, FB per round: all the 128-bit loads first, then the TMEM stores
+        int b0 = 0;
+#define TM_LDS128(B, J) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+" #J "*16];" : "=r"(v[B][4 * J]), "=r"(v[B][4 * J + 1]), "=r"(v[B][4 * J + 2]), "=r"(v[B][4 * J + 3]) : "r"(a))
+#define TM_LDBLOCK(B, BLK) { const unsigned a = row_addr + (tm_skew(lane_chunk + 4u * (unsigned)(BLK)) << 4); TM_LDS128(B, 0); TM_LDS128(B, 1); TM_LDS128(B, 2); TM_LDS128(B, 3); }
+        for (; b0 + (FB - 1) < nblocks; b0 += FB) {
           uint32_t v[FB][16];
 #pragma unroll
-          for (int b = 0; b < FB; ++b)
-            if (cb + 16 * b < p.SLOTW) {
-              const unsigned a = row_addr + (tm_skew(lane_chunk + (unsigned)((cb >> 2) + 4 * b)) << 4);
-#define TM_LDS128(J) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+" #J "*16];" : "=r"(v[b][4 * J]), "=r"(v[b][4 * J + 1]), "=r"(v[b][4 * J + 2]), "=r"(v[b][4 * J + 3]) : "r"(a))
-              TM_LDS128(0);
-              TM_LDS128(1);
-              TM_LDS128(2);
-              TM_LDS128(3);
-#undef TM_LDS128
-            }
+          for (int b = 0; b < FB; ++b) TM_LDBLOCK(b, b0 + b)
 #pragma unroll
-          for (int b = 0; b < FB; ++b)
-            if (cb + 16 * b < p.SLOTW) tm_st16(tcol + cb + 16 * b, v[b]);
+          for (int b = 0; b < FB; ++b) tm_st16(tcol + 16u * (unsigned)(b0 + b), v[b]);
         }
+        if (FB > 1 && b0 < nblocks) {  // tail: 1 .. FB-1 blocks
+          uint32_t v[FB][16];
+#pragma unroll
+          for (int b = 0; b < FB - 1; ++b)
+            if (b0 + b < nblocks) TM_LDBLOCK(b, b0 + b)
+#pragma unroll
+          for (int b = 0; b < FB - 1; ++b)
+            if (b0 + b < nblocks) tm_st16(tcol + 16u * (unsigned)(b0 + b), v[b]);
+        }
+#undef TM_LDBLOCK
+#undef TM_LDS128
       }
       tm_wait_st();
       tm_fence_before();
       __syncwarp();
       if (lane == 0) tm_mbar_arrive(tm_full + 8 * slot);
+      if (++slot == (unsigned)p.NSLOT) {
+        slot = 0;
+        ++round;
+      }
     }
     __syncwarp();
     if (lane == 0) tm_mbar_arrive(smem_empty + 8 * s);  // the producer's share; the compute warps still read the records
@@ -267,16 +327,16 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
-// warps 0 .. NCW-1: compute (TMEM lane quadrant = wid % 4, channel block = wid); warps NCW .. NCW+3: producers.
-template <int T, int OT, int NCW, int CREGS, int PREGS>
-__global__ void __launch_bounds__((NCW + 4) * 32, 1)
+// warps 0 .. NCW-1: compute (TMEM lane quadrant = wid % 4, channel block = wid); warps NCW .. NCW+NPW-1: producers.
+template <int T, int OT, int NCW, int NPW, int CREGS, int PREGS>
+__global__ void __launch_bounds__((NCW + NPW) * 32, 1)
     sconv_tmem_kernel(const TmParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias, int fuse_relu,
                       float *__restrict__ top, int nunits) {
   // setmaxnreg moves registers inside the CTA's OWN pool (what the launch allocated: R0 per thread), not the whole
   // register file: the compute warps can only grow by what the producer warps give back.  (Measured the hard way: a
   // split that needed the SM's unallocated registers left the last compute warpgroup spinning in setmaxnreg.inc.)
-  constexpr int R0 = 65536 / ((NCW + 4) * 32) / 8 * 8;
-  static_assert(NCW * (CREGS - R0) <= 4 * (R0 - PREGS), "setmaxnreg split exceeds the CTA register pool");
+  constexpr int R0 = 65536 / ((NCW + NPW) * 32) / 8 * 8;
+  static_assert(NCW * (CREGS - R0) <= NPW * (R0 - PREGS), "setmaxnreg split exceeds the CTA register pool");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const unsigned smem_base = (unsigned)__cvta_generic_to_shared(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
@@ -287,8 +347,8 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
 
   if (tid == 0) {
     for (int s = 0; s < p.NS; ++s) {
-      tm_mbar_init(smem_full + 8 * s, 128);        // every producer thread arrives through its cp.asyncs
-      tm_mbar_init(smem_empty + 8 * s, NCW + 4);   // every warp releases the stage
+      tm_mbar_init(smem_full + 8 * s, NPW * 32);     // every producer thread arrives through its cp.asyncs
+      tm_mbar_init(smem_empty + 8 * s, NCW + NPW);   // every warp releases the stage
     }
     for (int qq = 0; qq < 4; ++qq)
       for (int s = 0; s < p.NSLOT; ++s) {
@@ -308,7 +368,7 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
 
   if (wid >= NCW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS) : "memory");
-    tm_producer_loop<T, NCW, (PREGS >= 72 ? 3 : 2)>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
+    tm_producer_loop<T, NCW, NPW, (PREGS >= 72 ? 3 : PREGS >= 64 ? 2 : 1)>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS) : "memory");
     const int q = wid & 3;
@@ -349,19 +409,11 @@ __global__ void __launch_bounds__((NCW + 4) * 32, 1)
               unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
 #pragma unroll 1
               for (; n > 0; --n) {
-                uint32_t x[T];
-                tm_ld_window<T>(x, tslot + col);
-                unsigned long long w2;
-                asm volatile("mov.b64 %0, {%1, %1};" : "=l"(w2) : "r"(wbits));
+                const uint32_t taddr = tslot + col;
+                const unsigned w = wbits;
                 rp += 8;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
-                tm_wait_ld();
-#pragma unroll
-                for (int k = 0; k < T / 2; ++k) {
-                  unsigned long long xx;
-                  asm volatile("mov.b64 %0, {%1, %2};" : "=l"(xx) : "r"(x[2 * k]), "r"(x[2 * k + 1]));
-                  asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[o][k]) : "l"(w2), "l"(xx));
-                }
+                tm_tap<T>(acc[o], taddr, w);
               }
             }
           }

@@ -9,6 +9,10 @@ batch is sharded: every rank runs its own 256 images, no data-path collective (i
 
 Our arm prints ONE JSON line with
   value     images/s with the inputs resident in HBM (CUDA events, max over ranks),
+  parity    per layer: relative L2 of the TIMED plan's outputs (the autotuned kernel, 8 images) against the reference's
+            own CPU kernels (oracle/_ref); the run exits non-zero above 1e-4,
+  train     (default workload only) a short ResNet-50 forward + masked-backward step with the per-layer gradient
+            all-reduce issued through the library (escort_allreduce_grads on a real ncclComm_t, side stream),
   e2e       images/s through the C-ABI with HOST buffers: pinned-host -> device copies of every layer input that
             comes from outside the path and device -> host copies of its outputs inside the timed region,
   roofline  the dominant kernel against max(nnz-FLOPs / FP32-FMA peak, compulsory bytes / HBM bandwidth),
@@ -144,25 +148,35 @@ def cpu_reference_run(specs, sample, steps, warmup):
     return n * steps / dt, dt / steps * 1e3, int(threads), kind
 
 
+def _config(label, N, world):
+    """The workload as both arms name it (identical dict: the driver compares the two lines)."""
+    return {"workload": label, "batch_per_gpu": N, "global_batch": N * world}
+
+
+def cpu_reference_bounded(specs, steps, warmup, budget_s=120.0):
+    """One protocol for the reference arm and the cpu_baseline leg: the full batch per step unless the host is too slow
+    for the budget (calibrated on a 16-image slice)."""
+    sample = specs[0].N
+    ips, _, threads, kind = cpu_reference_run(specs, min(16, sample), 1, 1)
+    if sample / ips * (steps + warmup) > budget_s:
+        sample = max(8, int(budget_s * ips / (steps + warmup)))
+    ips, ms, threads, kind = cpu_reference_run(specs, sample, steps, warmup)
+    desc = "%d of %d images per step x %d steps (%d warm-up) through all %d layers, %s" % (
+        sample, specs[0].N, steps, warmup, len(specs),
+        "reference AVX2 sconv_unit_stride / caffe_cpu_sconv_default + OpenMP over images" if kind == "reference"
+        else "oracle C port + OpenMP over images")
+    return ips, ms, threads, kind, desc
+
+
 def run_reference(args, specs, label):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = specs[0].N if args.sample <= 0 else args.sample
-    # keep the whole run within a few minutes whatever the host: calibrate on a small slice first
-    ips, _, threads, kind = cpu_reference_run(specs, min(16, sample), 1, 1)
-    budget_s = 120.0
-    if sample / ips * (args.steps + args.warmup) > budget_s:
-        sample = max(8, int(budget_s * ips / (args.steps + args.warmup)))
-    ips, ms, threads, kind = cpu_reference_run(specs, sample, args.steps, args.warmup)
-    desc = "%d of %d images per step through all %d layers, %s" % (
-        sample, specs[0].N, len(specs),
-        "reference AVX2 sconv_unit_stride / caffe_cpu_sconv_default + OpenMP over images" if kind == "reference"
-        else "oracle C port + OpenMP over images")
+    ips, ms, threads, kind, desc = cpu_reference_bounded(specs, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": label, "batch_per_step": sample, "device": "host CPU"},
+            "dtype": "f32", "data": "synthetic", "config": _config(label, specs[0].N, args.gpus),
+            "detail": {"device": "host CPU", "threads": threads},
             "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
             "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -172,6 +186,207 @@ def run_reference(args, specs, label):
 # ----------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
+def _pin_to_gpu_numa(local):
+    """Run (and allocate pinned memory) on the cores NVML reports as local to this rank's GPU; returns the previous
+    affinity so that the CPU baseline can use the whole host again."""
+    try:
+        prev = os.sched_getaffinity(0)
+    except AttributeError:
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= prev
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+    return prev
+
+
+def _make_layers(specs, args, capi, wl, torch, train, tune_cache):
+    """WeightAlign through the C ABI -> plan -> tuning (measured once per layer shape, copied to the other layers of
+    the shape) -> device tensors.  Untimed set-up."""
+    layers, tuned = [], {}
+    dirty = False
+    for li, spec in enumerate(specs):
+        d = wl.make_layer_data(spec, li)
+        geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
+        csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)
+        plan = capi.Plan(geom, csr)
+        shape = (spec.Cin, spec.Cout, spec.H, spec.k, spec.stride, spec.pad, spec.group, round(spec.sparsity, 3))
+        if args.variant is not None:
+            plan.set_variant(args.variant)
+        elif shape in tuned:
+            plan.copy_tuning(tuned[shape])
+        elif spec.name in tune_cache and not train:
+            plan.set_config(*tune_cache[spec.name])
+        else:
+            plan.autotune(spec.N)
+            if train:
+                plan.autotune_backward(spec.N)
+            tuned[shape] = plan
+            tune_cache[spec.name] = list(plan.get_config())
+            dirty = True
+        x = torch.from_numpy(d["x"]).cuda()
+        b = torch.from_numpy(d["bias"]).cuda() if d["bias"] is not None else None
+        y = torch.empty((spec.N, spec.Cout, plan.Ho, plan.Wo), device="cuda")
+        flops, byts = wl.alg_work(spec, plan.nnz)
+        L = dict(spec=spec, plan=plan, x=x, b=b, y=y, flops=flops, bytes=byts, csr=csr, w=d["w"], bias=d["bias"], li=li)
+        if train:
+            g = torch.Generator(device="cuda").manual_seed(1701 + li)
+            L["dy"] = torch.rand(y.shape, device="cuda", generator=g) * 2 - 1
+            L["dx"] = torch.empty_like(x)
+            L["db"] = torch.zeros(spec.Cout, device="cuda") if b is not None else None
+            # CSR-ordered gradient in the reference's blob layout: group g at offset weight_offset * g
+            Mg, Cg = spec.Cout // spec.group, spec.Cin // spec.group
+            wo = Mg * Cg * spec.k * spec.k
+            rp = csr["rowptr"].cpu().numpy()
+            L["gsize"] = wo * (spec.group - 1) + int(rp[(Mg + 1) * spec.group - 1])
+        layers.append(L)
+    return layers, dirty
+
+
+def check_parity(layers, train, torch, capi):
+    """Outside the timed region: the outputs of the plans that were just timed (same kernels, same tilings) against
+    the reference's own CPU direct sparse conv on the first images of the batch (oracle/_ref; the C port if the
+    reference is not built).  Masked backward: against the oracle's restatement (the reference's backward is dense)."""
+    from oracle import pyoracle as po
+    po.build()
+    out = {}
+    for L in layers:
+        spec, plan = L["spec"], L["plan"]
+        n = min(8, spec.N)
+        g = po.Geom(n, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+        ocsr = po.weight_align(L["w"], g)
+        x8 = L["x"][:n].cpu().numpy()
+        relu = not train
+        if po.have_ref():
+            ref, _ = po.ref_conv_forward(x8, ocsr, g, L["bias"], relu=relu)
+        else:
+            ref = po.conv_forward(x8, ocsr, g, L["bias"], relu=relu)
+        res = {"fwd": po.rel_l2(L["y"][:n].cpu().numpy(), ref)}   # L["y"]: written by the last timed step
+        if train:
+            nb = min(2, n)
+            g2 = po.Geom(nb, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+            dy2 = L["dy"][:nb].contiguous()
+            wd = torch.zeros(L["w"].shape, device="cuda")
+            plan.backward_weight(L["x"][:nb].contiguous(), dy2, wd_dense=wd)
+            dx = plan.backward_data(dy2)
+            torch.cuda.synchronize()
+            wd_o, _, dx_o = po.conv_backward(x8[:nb], dy2.cpu().numpy(), L["w"], g2, mask_only=True, want_b=False)
+            res["bwd_weight"] = po.rel_l2(wd.cpu().numpy(), wd_o)
+            res["bwd_data"] = po.rel_l2(dx.cpu().numpy(), dx_o)
+        out[spec.name] = res
+    worst = max(v for r in out.values() for v in r.values())
+    return out, worst
+
+
+def run_train_leg(args, world, rank, torch, dist, capi, wl, barrier):
+    """BASELINE.json configs[3] under the driver's clock: ResNet-50 branch2b convs, forward + masked backward, the
+    gradient exchange issued per layer on a side stream through the library's own entry point with a real ncclComm_t
+    (NCCL<Dtype>::on_gradients_ready / run, src/caffe/parallel.cpp:202-256), weights broadcast once (:189-199)."""
+    specs = wl.RESNET50
+    layers, _ = _make_layers(specs, args, capi, wl, torch, True, {})
+    N = specs[0].N
+    offs, tot = [], 0
+    for L in layers:
+        offs.append(tot)
+        tot += (L["gsize"] + 3) // 4 * 4
+    flat = torch.zeros(tot, device="cuda")   # the flat diff buffer of the exchange (parallel.cpp:75-108)
+    for L, o in zip(layers, offs):
+        L["wd"] = flat[o:o + L["gsize"]]
+        L["wslice"] = flat[o:o + (L["gsize"] + 3) // 4 * 4]
+    comm = None
+    if world > 1:
+        def exchange_id(raw):
+            t = torch.tensor(list(raw) if raw is not None else [0] * 128, dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        comm = capi.NcclComm(world, rank, exchange_id)
+        # weights from rank 0 once, then the plans re-gather their values (every rank generated the same weights; the
+        # broadcast is the reference's start-up step, not a correction)
+        for L in layers:
+            wdev = torch.from_numpy(L["w"]).cuda()
+            capi.broadcast(wdev, 0, comm)
+            L["plan"].refresh_values(wdev)
+        torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    ev_bwd = torch.cuda.Event(enable_timing=True)
+    ev_all = torch.cuda.Event(enable_timing=True)
+
+    def step(mark=False):
+        for L in layers:
+            L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"])
+        for L in reversed(layers):
+            L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"], accumulate=False)
+            if L["db"] is not None:
+                capi.bias_backward(L["dy"], L["db"])
+            if comm is not None:
+                # this layer's gradient is final: reduce it on the side stream while the next layers' backward runs
+                e = torch.cuda.Event()
+                e.record(main)
+                side.wait_event(e)
+                capi.allreduce_grads(L["wslice"], 1.0 / world, comm, stream=side)
+            L["plan"].backward_data(L["dy"], L["dx"])
+        if mark:
+            ev_bwd.record(main)
+        if comm is not None:
+            main.wait_stream(side)
+        if mark:
+            ev_all.record(main)
+
+    steps, warm = 3, 2
+    for _ in range(warm):
+        step()
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(steps):
+        step(mark=(s == steps - 1))
+    t1.record()
+    barrier()
+    ms = t0.elapsed_time(t1) / steps
+    exposed = ev_bwd.elapsed_time(ev_all)
+    # the exchange alone (same buffers, nothing to overlap with): bus bandwidth of the flat all-reduce
+    bus = None
+    exch_ms = 0.0
+    if comm is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        capi.allreduce_grads(flat, 1.0, comm)
+        barrier()
+        e0.record()
+        for _ in range(5):
+            capi.allreduce_grads(flat, 1.0, comm)
+        e1.record()
+        torch.cuda.synchronize()
+        exch_ms = e0.elapsed_time(e1) / 5
+        bus = 2.0 * (world - 1) / world * flat.numel() * 4 / (exch_ms * 1e-3) / 1e9
+    if world > 1:
+        t = torch.tensor([ms, exposed], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, exposed = float(t[0].item()), float(t[1].item())
+    parity, worst = check_parity(layers, True, torch, capi) if rank == 0 else ({}, 0.0)
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.destroy()
+    flops = sum(L["flops"] for L in layers) * 3
+    return {"workload": "resnet50_branch2b_3x3_pruned70_fwd+masked-bwd_b256", "value": world * N / (ms * 1e-3), "unit": UNIT,
+            "ms_per_step": ms, "steps": steps, "warmup": warm, "tflops": flops / ms / 1e9,
+            "exchange": {"through": "escort_allreduce_grads(ncclComm_t) per layer on a side stream, 1/N fused behind it"
+                                    if comm is not None else "single rank: no exchange",
+                         "allreduce_bytes_per_step": flat.numel() * 4 if comm is not None else 0,
+                         "exposed_ms": exposed if comm is not None else 0.0,
+                         "standalone_ms": exch_ms, "bus_gbs": bus},
+            "kernels": {"fwd": layers[0]["plan"].kernel_names()["fwd"], "bwd_data": layers[0]["plan"].kernel_names()["bwd_data"],
+                        "bwd_weight": layers[0]["plan"].kernel_names()["bwd_weight"]},
+            "parity": parity, "parity_worst": worst}
+
+
 def run_ours(args, specs, label):
     import torch
     import torch.distributed as dist
@@ -183,6 +398,7 @@ def run_ours(args, specs, label):
         raise SystemExit("bench.py: no CUDA device -- the sparse-conv path has no CPU fallback "
                          "(use --impl reference for the CPU reference arm)")
     torch.cuda.set_device(local)
+    full_affinity = _pin_to_gpu_numa(local)   # before any pinned allocation: host buffers local to this rank's GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL prints its version banner to stdout when the first communicator comes up; stdout carries ONE JSON line,
@@ -209,59 +425,30 @@ def run_ours(args, specs, label):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- FP32 FMA peak, measured live (not in MEASURED_PEAKS.json) ----
+    # ---- FP32 FMA peak, measured live by this run (builder-measured: MEASURED_PEAKS.json has no fp32 entry) ----
     fp32_peaks = {}
     for v, name in ((0, "ffma_shared_operand"), (1, "ffma2_packed"), (2, "ffma_3reg")):
         fp32_peaks[name] = capi.measure_fp32_peak(v, 8192)[0]
     fp32_peak = max(fp32_peaks.values())
     hbm_peak, hbm_src = _peaks()
 
-    # ---- set-up (untimed): weights -> CSR through the C ABI (WeightAlign) -> plan, autotuned at the batch size ----
-    layers = []
-    host_in, host_out = [], []
-    tune_cache, tune_dirty = {}, False
+    # ---- set-up (untimed) ----
+    tune_cache = {}
     if args.tune_cache and os.path.exists(args.tune_cache):
         tune_cache = json.load(open(args.tune_cache))
-    for li, spec in enumerate(specs):
-        d = wl.make_layer_data(spec, li)
-        geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
-        csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)
-        plan = capi.Plan(geom, csr)
-        if args.variant is not None:
-            plan.set_variant(args.variant)
-        elif spec.name in tune_cache:
-            plan.set_config(*tune_cache[spec.name])
-        else:
-            plan.autotune(spec.N)
-            tune_cache[spec.name] = list(plan.get_config())
-            tune_dirty = True
-        if args.train and args.variant is None:
-            plan.autotune_backward(spec.N)
-        x = torch.from_numpy(d["x"]).cuda()
-        b = torch.from_numpy(d["bias"]).cuda() if d["bias"] is not None else None
-        y = torch.empty((spec.N, spec.Cout, plan.Ho, plan.Wo), device="cuda")
-        flops, byts = wl.alg_work(spec, plan.nnz)
-        layers.append(dict(spec=spec, plan=plan, x=x, b=b, y=y, flops=flops, bytes=byts, csr=csr))
-        host_in.append(torch.from_numpy(d["x"]).pin_memory())
-        host_out.append(torch.empty(y.shape, dtype=torch.float32).pin_memory())
-        if args.train:
-            Lr = layers[-1]
-            g = torch.Generator(device="cuda").manual_seed(1701 + li)
-            Lr["dy"] = torch.rand(y.shape, device="cuda", generator=g) * 2 - 1
-            Lr["dx"] = torch.empty_like(x)
-            Lr["db"] = torch.zeros(spec.Cout, device="cuda") if b is not None else None
-            # CSR-ordered gradient in the reference's blob layout: group g at offset weight_offset * g
-            Mg, Cg = spec.Cout // spec.group, spec.Cin // spec.group
-            wo = Mg * Cg * spec.k * spec.k
-            rp = csr["rowptr"].cpu().numpy()
-            Lr["gsize"] = wo * (spec.group - 1) + int(rp[(Mg + 1) * spec.group - 1])
-            host_in.append(Lr["dy"].cpu().pin_memory())
-            host_out.append(torch.empty(x.shape, dtype=torch.float32).pin_memory())
+    layers, tune_dirty = _make_layers(specs, args, capi, wl, torch, args.train, tune_cache)
     if args.tune_cache and tune_dirty and rank == 0:
         os.makedirs(os.path.dirname(os.path.abspath(args.tune_cache)), exist_ok=True)
         json.dump(tune_cache, open(args.tune_cache, "w"))
     N = specs[0].N
     nl = len(layers)
+    host_in, host_out = [], []
+    for L in layers:
+        host_in.append(L["x"].cpu().pin_memory())
+        host_out.append(torch.empty(L["y"].shape, dtype=torch.float32).pin_memory())
+        if args.train:
+            host_in.append(L["dy"].cpu().pin_memory())
+            host_out.append(torch.empty(L["x"].shape, dtype=torch.float32).pin_memory())
 
     # the step as a list of timed operations: (layer index, kind, callable); every operation is one launch of ours
     flat = None
@@ -283,17 +470,24 @@ def run_ours(args, specs, label):
                                                                                accumulate=False)))
             ops.append((i, "bwd_data", lambda L=L: L["plan"].backward_data(L["dy"], L["dx"])))
     nops = len(ops)
+    comm = None
+    if args.train and world > 1:
+        def exchange_id(raw):
+            t = torch.tensor(list(raw) if raw is not None else [0] * 128, dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, 0)
+            return bytes(t.cpu().tolist())
+        comm = capi.NcclComm(world, rank, exchange_id)
 
     def exchange():
-        # the path's one exchange step: sum over ranks, then 1/N (NCCL<Dtype>::on_gradients_ready, parallel.cpp:238-256)
+        # the path's one exchange step: sum over ranks, then 1/N (NCCL<Dtype>::on_gradients_ready, parallel.cpp:238-256),
+        # through the library's own entry point on a real ncclComm_t
         if not args.train:
             return
         for L in layers:
             if L["db"] is not None:
                 capi.bias_backward(L["dy"], L["db"])
-        if world > 1:
-            dist.all_reduce(flat)
-            capi.allreduce_grads(flat, 1.0 / world)
+        if comm is not None:
+            capi.allreduce_grads(flat, 1.0 / world, comm)
 
     def step(events=None):
         for k, (i, kind, fn) in enumerate(ops):
@@ -328,6 +522,9 @@ def run_ours(args, specs, label):
     value = world * N * args.steps / (ms_total * 1e-3)
     op_ms = [float(np.mean([evs[s][k][0].elapsed_time(evs[s][k][1]) for s in range(args.steps)])) for k in range(nops)]
 
+    # ---- parity of what was just timed (rank 0; outside the timed region) ----
+    parity, parity_worst = (check_parity(layers, args.train, torch, capi) if rank == 0 and not args.no_parity else ({}, 0.0))
+
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region, chunk-pipelined over streams ----
     nchunk = 4 if N % 4 == 0 else 1
     cs = N // nchunk
@@ -340,7 +537,7 @@ def run_ours(args, specs, label):
         d2h = sum(L["dx"].numel() * 4 for L in layers) + flat.numel() * 4
         host_flat = torch.empty(flat.shape, dtype=torch.float32).pin_memory()
 
-    def e2e_step():
+    def e2e_step(kernels=True):
         if args.train:
             # host bottom + top_diff in, bottom_diff + the reduced flat gradient out; one stream per layer, round robin
             for i, L in enumerate(layers):
@@ -348,13 +545,15 @@ def run_ours(args, specs, label):
                 with torch.cuda.stream(st):
                     L["x"].copy_(host_in[2 * i], non_blocking=True)
                     L["dy"].copy_(host_in[2 * i + 1], non_blocking=True)
-                    L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"], stream=st)
-                    L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"], accumulate=False, stream=st)
-                    L["plan"].backward_data(L["dy"], L["dx"], stream=st)
+                    if kernels:
+                        L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"], stream=st)
+                        L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"], accumulate=False, stream=st)
+                        L["plan"].backward_data(L["dy"], L["dx"], stream=st)
                     host_out[2 * i + 1].copy_(L["dx"], non_blocking=True)
             for st in streams:
                 st.synchronize()
-            exchange()
+            if kernels:
+                exchange()
             host_flat.copy_(flat, non_blocking=True)
             torch.cuda.current_stream().synchronize()
             return
@@ -366,25 +565,42 @@ def run_ours(args, specs, label):
                 with torch.cuda.stream(st):
                     sl = slice(c * cs, (c + 1) * cs)
                     L["x"][sl].copy_(host_in[i][sl], non_blocking=True)
-                    L["plan"].forward(L["x"][sl], L["b"], relu=True, top=L["y"][sl], stream=st)
+                    if kernels:
+                        L["plan"].forward(L["x"][sl], L["b"], relu=True, top=L["y"][sl], stream=st)
                     host_out[i][sl].copy_(L["y"][sl], non_blocking=True)
         for st in streams:
             st.synchronize()
 
-    for _ in range(max(1, min(args.warmup, 3))):
-        e2e_step()
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    e2e_s = time.perf_counter() - w0
-    if world > 1:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * N * args.steps / e2e_s
+    def timed_e2e(kernels):
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step(kernels)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step(kernels)
+        barrier()
+        dt = time.perf_counter() - w0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * N * args.steps / dt
 
+    e2e_value = timed_e2e(True)
+    copy_ceiling = timed_e2e(False)   # the same host <-> device bytes with no kernel at all: what the host links allow
+
+    # ---- config 4 under the same clock: a short ResNet-50 training step with the library-issued exchange ----
+    train_leg = None
+    if not args.train and args.workload == "alexnet" and not args.no_train_leg and args.variant is None:
+        for L in layers:          # free the forward workload's device tensors first
+            L["x"] = L["y"] = None
+        del host_in, host_out
+        torch.cuda.empty_cache()
+        train_leg = run_train_leg(args, world, rank, torch, dist, capi, wl, barrier)
+
+    if comm is not None:
+        torch.cuda.synchronize()
+        comm.destroy()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -408,11 +624,13 @@ def run_ours(args, specs, label):
     roofline = {"bound": "fp32_fma" if t_fma >= t_hbm else "hbm", "kernel": dom_kernel, "op": ops[dom][1],
                 "layer": L["spec"].name, "achieved": L["flops"] / t_meas / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": max(t_fma, t_hbm) / t_meas,
-                "peak_source": "FP32 FMA: measured live by escort_measure_fp32_peak (best of FFMA / FFMA2 "
-                               "register-resident loops); HBM: " + hbm_src,
+                "peak_source": "FP32 FMA: builder-measured, live in this run, by escort_measure_fp32_peak (best of FFMA / "
+                               "FFMA2 register-resident loops; MEASURED_PEAKS.json has no fp32 entry); HBM: " + hbm_src,
                 "alg_flops_per_launch": L["flops"], "alg_bytes_per_launch": L["bytes"],
                 "launch_ms": op_ms[dom], "hbm_achieved_gbs": L["bytes"] / t_meas / 1e9, "hbm_peak_gbs": hbm_peak,
-                "traffic": traffic, "fp32_peaks_tflops": fp32_peaks}
+                "traffic": traffic, "fp32_peaks_tflops": fp32_peaks,
+                "step_weighted_frac": sum(max(Lr["flops"] / (fp32_peak * 1e12), Lr["bytes"] / (hbm_peak * 1e9))
+                                          for (i, _, _) in ops for Lr in [layers[i]]) / (sum(op_ms) * 1e-3)}
     per_layer = []
     for k, (i, kind, _) in enumerate(ops):
         Lr = layers[i]
@@ -421,38 +639,44 @@ def run_ours(args, specs, label):
                           "images_per_s": N / (op_ms[k] * 1e-3), "tflops": Lr["flops"] / op_ms[k] / 1e9,
                           "roofline_frac": max(tf, th) / (op_ms[k] * 1e-3), "nnz": int(Lr["plan"].nnz)})
 
-    # ---- cpu_baseline (N = 1 only): the reference's CPU path on this host, bounded sample ----
+    # ---- cpu_baseline (N = 1 only): the reference's CPU path on this host, the reference arm's own protocol ----
     cpu = None
     if world == 1 and not args.no_cpu:
         try:
-            sample = min(N, 64)
-            ips, ms, threads, kind = cpu_reference_run(specs, sample, 3, 1)
+            if full_affinity:
+                os.sched_setaffinity(0, full_affinity)   # the CPU baseline gets the whole host
+            ips, ms, threads, kind, desc = cpu_reference_bounded(specs, args.steps, args.warmup, budget_s=60.0)
             cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
-                   "sample": "%d of %d images x 3 steps through all %d layers (reference CPU direct sconv, "
-                             "OpenMP over images)%s" % (sample, N, nl, "; forward only -- the reference's CPU backward is "
-                             "im2col + BLAS GEMM, which this image cannot build" if args.train else "")}
+                   "sample": desc + ("; forward only -- the reference's CPU backward is im2col + BLAS GEMM, which this "
+                                     "image cannot build" if args.train else "")}
         except Exception as e:  # the baseline is reported, never required
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
 
+    train_launches = (nops + (sum(1 for L in layers if L["b"] is not None) + nl + (1 if world > 1 else 0)
+                              if args.train else 0)) * args.steps
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": label, "batch_per_gpu": N, "global_batch": N * world, "parallelism": "batch-shard x%d, "
-                       "no data-path collective" % world if not args.train else
-                       "batch-shard x%d, NCCL all-reduce of the flat CSR-ordered gradient (%d floats) + 1/N scale" % (world, flat.numel()),
+            "data": "synthetic", "config": _config(label, N, world),
+            "detail": {"parallelism": "batch-shard x%d, no data-path collective" % world if not args.train else
+                       "batch-shard x%d, ncclAllReduce of the flat CSR-ordered gradient (%d floats) + 1/N scale through "
+                       "escort_allreduce_grads" % (world, flat.numel()),
                        "epilogue": "bias+ReLU fused" if not args.train else "bias fused (training step: no ReLU)",
                        "l2": "inputs+outputs of one step (%.0f MB) exceed the 126 MB L2, so every step re-reads HBM"
                              % (sum(Lr["bytes"] for Lr in layers) / 1e6)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "how": ("pinned host -> device, C-ABI forward, device -> pinned host; %d-image chunks over 4 streams" % cs)
+                    "copy_ceiling": copy_ceiling,
+                    "how": ("pinned host (allocated on the GPU's NUMA node) -> device, C-ABI forward, device -> pinned host; "
+                            "%d-image chunks over 4 streams; copy_ceiling = the same copies with no kernels" % cs)
                            if not args.train else "pinned host bottom + top_diff -> device, C-ABI forward + backward_weight + "
                            "backward_data per layer (4 streams), gradient exchange, bottom_diff + flat gradient -> pinned host"},
-            "gpu_launches": (nops + (sum(1 for L in layers if L["b"] is not None) + nl + (1 if world > 1 else 0)
-                                     if args.train else 0)) * args.steps, "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
-            "layers": per_layer}
+            "gpu_launches": train_launches, "roofline": roofline, "parity": parity, "parity_worst": parity_worst,
+            "cpu_baseline": cpu, "clocks": clocks, "layers": per_layer, "train": train_leg}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+    bad = max(parity_worst, train_leg["parity_worst"] if train_leg else 0.0)
+    if bad > 1e-4:
+        raise SystemExit("bench.py: parity FAILED: worst relative L2 %.3e > 1e-4 against the reference CPU kernels" % bad)
 
 
 def main():
@@ -462,9 +686,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="alexnet", choices=["alexnet", "googlenet", "resnet50", "lenet"])
-    ap.add_argument("--sample", type=int, default=0, help="reference arm: images per step (0 = the full batch)")
     ap.add_argument("--variant", type=int, default=None, help="force a forward variant instead of autotuning")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed outputs")
+    ap.add_argument("--no-train-leg", action="store_true", help="default workload: skip the short ResNet-50 training step")
     ap.add_argument("--train", action="store_true",
                     help="step = forward + masked backward (weight, data, bias) of every layer + the gradient all-reduce "
                          "(BASELINE.json configs[3]); default: forward only")

@@ -41,6 +41,7 @@ lib.escort_plan_set_config.argtypes = [C.c_void_p, C.c_int, C.c_int]
 lib.escort_plan_get_config.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
 lib.escort_plan_autotune.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_autotune_backward.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.escort_plan_copy_tuning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.escort_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
 
 
@@ -175,6 +176,9 @@ class Plan:
     def autotune(self, num, stream=None):
         _check(lib.escort_plan_autotune(self.h, int(num), _stream(stream)), "escort_plan_autotune")
 
+    def copy_tuning(self, other, stream=None):
+        _check(lib.escort_plan_copy_tuning(self.h, other.h, _stream(stream)), "escort_plan_copy_tuning")
+
     def autotune_backward(self, num, stream=None):
         _check(lib.escort_plan_autotune_backward(self.h, int(num), _stream(stream)), "escort_plan_autotune_backward")
 
@@ -229,8 +233,39 @@ def sconv_padded(fuse_relu, num, inp, ifmap_size, rowptr, colidx, values, bias, 
 
 
 def allreduce_grads(flat, scale, comm=None, stream=None):
-    _check(lib.escort_allreduce_grads(C.c_void_p(comm or 0), _ptr(flat), C.c_size_t(flat.numel()), C.c_float(scale),
+    """ncclAllReduce(sum) over `flat` on `comm` (an NcclComm, a raw ncclComm_t address, or None = scale only), then * scale."""
+    handle = comm.handle if isinstance(comm, NcclComm) else (comm or 0)
+    _check(lib.escort_allreduce_grads(C.c_void_p(handle), _ptr(flat), C.c_size_t(flat.numel()), C.c_float(scale),
                                       _stream(stream)), "escort_allreduce_grads")
+
+
+def broadcast(buf, root, comm, stream=None):
+    handle = comm.handle if isinstance(comm, NcclComm) else comm
+    _check(lib.escort_broadcast(C.c_void_p(handle), _ptr(buf), C.c_size_t(buf.numel()), int(root), _stream(stream)),
+           "escort_broadcast")
+
+
+class NcclComm:
+    """An ncclComm_t created through the library's own bring-up entries (escort_comm_unique_id / _init_rank).
+    `exchange_id(id_bytes_or_None) -> id_bytes` ships rank 0's 128-byte id to every rank (e.g. a torch.distributed or
+    MPI broadcast); with nranks == 1 no exchange is needed."""
+
+    def __init__(self, nranks=1, rank=0, exchange_id=None):
+        buf = (C.c_char * 128)()
+        if rank == 0:
+            _check(lib.escort_comm_unique_id(buf), "escort_comm_unique_id")
+        raw = bytes(buf)
+        if nranks > 1:
+            raw = exchange_id(raw if rank == 0 else None)
+        buf = (C.c_char * 128).from_buffer_copy(raw)
+        h = C.c_void_p(0)
+        _check(lib.escort_comm_init_rank(C.byref(h), nranks, buf, rank), "escort_comm_init_rank")
+        self.handle, self.nranks, self.rank = h.value, nranks, rank
+
+    def destroy(self):
+        if getattr(self, "handle", None):
+            lib.escort_comm_destroy(C.c_void_p(self.handle))
+            self.handle = None
 
 
 def measure_fp32_peak(variant=0, iters=4096):

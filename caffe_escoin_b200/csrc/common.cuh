@@ -94,6 +94,7 @@ int tile_bwdw_autotune(escort_plan *plan, int num, cudaStream_t stream);
 int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_diff, float *wd_dense, float *wd_csr,
               int accumulate, cudaStream_t stream);
 const char *tile_kernel_name(const TilePlan *tp);
+int tile_plan_variant(const TilePlan *tp);  // 1-based variant id of a built plan
 int tile_num_variants();
 bool tile_variant_applies(const escort_plan *plan, int variant);  // variant = 1-based index
 int tile_regather(escort_plan *plan, const int4 *meta, cudaStream_t stream);

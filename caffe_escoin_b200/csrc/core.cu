@@ -625,6 +625,34 @@ static int autotune_one(escort_plan *p, int num, cudaStream_t stream) {
   return escort_plan_set_config(p, best_v, best_rank);
 }
 
+// Apply the tuning of another plan of the same geometry (forward variant + layout, backward-data sub-plan, backward
+// weight variant) without measuring again: layers of one shape (ResNet-50 has 16 branch2b convs in 4 shapes) are
+// tuned once.
+extern "C" int escort_plan_copy_tuning(escort_plan *dst, const escort_plan *src, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(dst && src, "escort_plan_copy_tuning: null plan");
+  ESCORT_REQUIRE(memcmp(&dst->g, &src->g, sizeof(escort_geom)) == 0, "escort_plan_copy_tuning: geometries differ");
+  int rc = escort_plan_set_config(dst, src->variant, src->layout_rank);
+  if (rc) return rc;
+  if (src->bwd) {
+    if (!dst->bwd && !dst->bwd_tried) {
+      rc = build_bwd_plan(dst, stream);
+      if (rc) return rc;
+    }
+    if (dst->bwd) {
+      rc = escort_plan_set_config(dst->bwd, src->bwd->variant, src->bwd->layout_rank);
+      if (rc) return rc;
+    }
+  }
+  if (src->tile_w) {
+    dst->tile_w_tried = 1;
+    rc = tile_bwdw_build(dst, stream, tile_plan_variant(src->tile_w));
+    if (rc) return rc;
+    ESCORT_CUDA(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
 extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");

@@ -107,6 +107,7 @@ void tile_plan_free(TilePlan *tp) {
 }
 
 const char *tile_kernel_name(const TilePlan *tp) { return tp->name; }
+int tile_plan_variant(const TilePlan *tp) { return tp->vidx + 1; }
 int tile_num_variants() { return kNumVariants + tmem_num_variants(); }
 bool tile_variant_applies(const escort_plan *plan, int variant) {
   if (variant > kNumVariants) return tmem_variant_applies(plan, variant - kNumVariants - 1);
@@ -775,6 +776,7 @@ int tile_bwdw_build(escort_plan *plan, cudaStream_t stream, int variant) {
     plan->tile_w = nullptr;
   }
   TilePlan *fwd = plan->tile;
+  TmemPlan *fwd_tm = plan->tm;  // tile_plan_build clears both forward slots
   const int rank = plan->layout_rank;
   plan->layout_rank = 0;
   g_building_w = true;
@@ -782,6 +784,7 @@ int tile_bwdw_build(escort_plan *plan, cudaStream_t stream, int variant) {
   g_building_w = false;
   plan->tile_w = plan->tile;
   plan->tile = fwd;
+  plan->tm = fwd_tm;
   plan->layout_rank = rank;
   if (rc == 0 && plan->tile_w) {
     // per-tap destinations (stream order), so that the flush needs one index load per tap instead of two dependent ones

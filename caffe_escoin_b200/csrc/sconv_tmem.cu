@@ -123,9 +123,10 @@ int tmem_choose_variant(const escort_plan *plan) {
   const escort_geom &g = plan->g;
   const int Cg = g.channels / g.group;
   const double density = (double)plan->nnz / ((double)g.num_output * Cg * g.kernel_h * g.kernel_w);
-  // low density: the window fill (shared-memory bandwidth) is the bound, so more output channels per staged window
-  // (T = 16); otherwise fewer instructions per FMA (T = 32)
-  const int prefs[2] = {density * g.kernel_h * g.kernel_w < 1.6 ? 0 : 1, 0};
+  // measured on B200 (profiles/r02_tmem_variant_sweep.txt): few taps per staged window (AlexNet 3x3 at 12 %: about one
+  // per output channel and input channel) -> fewer, fatter compute warps (8 output channels each); otherwise 16 warps
+  const double taps_per_window = density * g.kernel_h * g.kernel_w;
+  const int prefs[2] = {taps_per_window < 1.6 ? 4 : 0, 0};
   for (int tv : prefs)
     if (tmem_variant_applies(plan, tv)) return tv;
   for (int tv = 0; tv < kNumTmVariants; ++tv)
@@ -144,7 +145,8 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   const int PW = g.width + g.pad_w, IMGR = g.height + g.pad_h, IMG = IMGR * PW;
   const int HALO = (KH - 1) * g.dilation_h * PW + (KW - 1) * g.dilation_w;
   const int SLOTW = round_up(T + HALO, 16);
-  int CHS = std::max(1, std::min(4, 512 / (4 * SLOTW)));
+  int CHS = std::max(1, std::min(4, 512 / (3 * SLOTW)));  // three slot groups in flight; larger groups = fewer hand-shakes per tap
+  if (const char *e = getenv("ESCORT_TM_CHS")) CHS = std::max(1, std::min(atoi(e), 512 / (2 * SLOTW)));  // tuning knob
   while (CHS > 1 && CHS * KH * KW > 255) --CHS;
   const int NSLOT = std::min(512 / (CHS * SLOTW), kTmMaxSlots);
   if (NSLOT < 2) return 0;

@@ -61,16 +61,20 @@ __device__ __forceinline__ void tm_mbar_wait(unsigned addr, unsigned parity, int
                : "r"(addr), "r"(parity)
                : "memory");
   if (ok) return;
-  unsigned long long t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  unsigned long long t0 = 0;
   for (;;) {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(addr), "r"(parity)
-                 : "memory");
-    if (ok) return;
+    // 64 cheap polls (try_wait suspends the warp until the barrier is touched or the hint expires), then one look at the clock
+#pragma unroll 1
+    for (int i = 0; i < 64; ++i) {
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(ok)
+                   : "r"(addr), "r"(parity)
+                   : "memory");
+      if (ok) return;
+    }
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t0 == 0) t0 = t1;
     if (t1 - t0 > 2000000000ull) {
       if (dbg && (threadIdx.x & 31) == 0 && atomicCAS(dbg, 0, code) == 0) {
         dbg[1] = (int)blockIdx.x;
@@ -154,6 +158,35 @@ __device__ __forceinline__ void tm_tap<32>(unsigned long long (&a)[16], uint32_t
         "+l"(a[10]), "+l"(a[11]), "+l"(a[12]), "+l"(a[13]), "+l"(a[14]), "+l"(a[15])
       : "r"(taddr), "r"(wbits)
       : "memory");
+}
+// Two nonzeros of the same output-channel slot: both window loads are issued before the first FMA, so the second
+// load's latency hides behind the first tap's FMAs (the accumulation order stays a-then-b: bit-identical to two taps).
+template <int T>
+__device__ __forceinline__ void tm_tap2(unsigned long long (&acc)[T / 2], uint32_t ta, unsigned wa, uint32_t tb, unsigned wb);
+template <>
+__device__ __forceinline__ void tm_tap2<16>(unsigned long long (&a)[8], uint32_t ta, unsigned wa, uint32_t tb, unsigned wb) {
+  asm volatile(
+      "{\n\t.reg .b32 t<16>, u<16>;\n\t.reg .b64 p<8>, q<8>, w2, v2;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}, [%8];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {u0,u1,u2,u3,u4,u5,u6,u7,u8,u9,u10,u11,u12,u13,u14,u15}, [%10];\n\t"
+      "mov.b64 w2, {%9, %9};\n\tmov.b64 v2, {%11, %11};\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      "mov.b64 p0, {t0, t1};\n\tmov.b64 p1, {t2, t3};\n\tmov.b64 p2, {t4, t5};\n\tmov.b64 p3, {t6, t7};\n\t"
+      "mov.b64 p4, {t8, t9};\n\tmov.b64 p5, {t10, t11};\n\tmov.b64 p6, {t12, t13};\n\tmov.b64 p7, {t14, t15};\n\t"
+      "mov.b64 q0, {u0, u1};\n\tmov.b64 q1, {u2, u3};\n\tmov.b64 q2, {u4, u5};\n\tmov.b64 q3, {u6, u7};\n\t"
+      "mov.b64 q4, {u8, u9};\n\tmov.b64 q5, {u10, u11};\n\tmov.b64 q6, {u12, u13};\n\tmov.b64 q7, {u14, u15};\n\t"
+      "fma.rn.f32x2 %0, w2, p0, %0;\n\tfma.rn.f32x2 %1, w2, p1, %1;\n\tfma.rn.f32x2 %2, w2, p2, %2;\n\tfma.rn.f32x2 %3, w2, p3, %3;\n\t"
+      "fma.rn.f32x2 %4, w2, p4, %4;\n\tfma.rn.f32x2 %5, w2, p5, %5;\n\tfma.rn.f32x2 %6, w2, p6, %6;\n\tfma.rn.f32x2 %7, w2, p7, %7;\n\t"
+      "fma.rn.f32x2 %0, v2, q0, %0;\n\tfma.rn.f32x2 %1, v2, q1, %1;\n\tfma.rn.f32x2 %2, v2, q2, %2;\n\tfma.rn.f32x2 %3, v2, q3, %3;\n\t"
+      "fma.rn.f32x2 %4, v2, q4, %4;\n\tfma.rn.f32x2 %5, v2, q5, %5;\n\tfma.rn.f32x2 %6, v2, q6, %6;\n\tfma.rn.f32x2 %7, v2, q7, %7;\n\t}"
+      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7])
+      : "r"(ta), "r"(wa), "r"(tb), "r"(wb)
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tm_tap2<32>(unsigned long long (&a)[16], uint32_t ta, unsigned wa, uint32_t tb, unsigned wb) {
+  tm_tap<32>(a, ta, wa);  // 32-column windows: 64 more registers for the pair are not available; one after the other
+  tm_tap<32>(a, tb, wb);
 }
 __device__ __forceinline__ void tm_st16(uint32_t taddr, const uint32_t (&r)[16]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
@@ -407,13 +440,23 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
 #pragma unroll
             for (int o = 0; o < OT; ++o) {
               unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
-#pragma unroll 1
-              for (; n > 0; --n) {
+              // (col, wbits) always hold the NEXT record; an odd tap first, then pairs (half the loop overhead per tap)
+              if (n & 1u) {
                 const uint32_t taddr = tslot + col;
                 const unsigned w = wbits;
                 rp += 8;
                 asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
                 tm_tap<T>(acc[o], taddr, w);
+              }
+#pragma unroll 1
+              for (n >>= 1; n > 0; --n) {
+                const uint32_t ta = tslot + col;
+                const unsigned wa = wbits;
+                unsigned colb, wb;
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(colb), "=r"(wb) : "r"(rp));
+                asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+16];" : "=r"(col), "=r"(wbits) : "r"(rp));
+                rp += 16;
+                tm_tap2<T>(acc[o], ta, wa, tslot + colb, wb);
               }
             }
           }

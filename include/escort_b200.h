@@ -117,6 +117,8 @@ ESCORT_API int escort_plan_autotune(escort_plan *plan, int num, escort_stream_t 
  * weights -- ConvolutionLayer::Backward_gpu's backward_gpu_gemm + col2im, src/caffe/layers/conv_layer.cu:64-68);
  * a no-op for geometries that use the generic backward kernel.  Training hosts call it once after WeightAlign. */
 ESCORT_API int escort_plan_autotune_backward(escort_plan *plan, int num, escort_stream_t stream);
+/* apply another plan's tuning (same geometry) instead of measuring again */
+ESCORT_API int escort_plan_copy_tuning(escort_plan *dst, const escort_plan *src, escort_stream_t stream);
 
 /* ---- a5-a9: native forward ---------------------------------------------------------------------------------
  * Replaces the whole per-image sequence of ConvolutionLayer::Forward_gpu in SCONV / SCONV_PAR mode
@@ -154,6 +156,14 @@ ESCORT_API int escort_refresh_values(escort_plan *plan, const float *weights_den
  * Replaces NCCL<Dtype>::on_gradients_ready (src/caffe/parallel.cpp:238-256): ncclAllReduce(sum) over the
  * flat diff buffer, then scale by `scale` (1/solver_count).  `comm` is an ncclComm_t passed as void*. */
 ESCORT_API int escort_allreduce_grads(void *comm, float *flat, size_t count, float scale, escort_stream_t stream);
+/* Weight broadcast from `root` before the first step (NCCL<Dtype>::Broadcast, src/caffe/parallel.cpp:189-199). */
+ESCORT_API int escort_broadcast(void *comm, float *buf, size_t count, int root, escort_stream_t stream);
+/* Communicator bring-up for hosts without an NCCL binding of their own (a Caffe host passes the ncclComm_t it already
+ * owns, src/caffe/parallel.cpp:141-171): rank 0 fills a 128-byte ncclUniqueId, ships it to the other ranks by any
+ * means, every rank calls init_rank.  One process per GPU; the current CUDA device is the rank's device. */
+ESCORT_API int escort_comm_unique_id(void *id128);
+ESCORT_API int escort_comm_init_rank(void **comm_out, int nranks, const void *id128, int rank);
+ESCORT_API int escort_comm_destroy(void *comm);
 
 /* ---- misc ---------------------------------------------------------------------------------------------------- */
 /* register-resident FFMA microbenchmark used for the FP32 roofline denominator;

@@ -24,9 +24,10 @@ class Geom(C.Structure):
 EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sconv_padded", "escort_plan_create",
            "escort_plan_destroy", "escort_plan_nnz", "escort_plan_kernel_name", "escort_plan_describe",
            "escort_plan_set_variant", "escort_plan_set_config", "escort_plan_get_config", "escort_plan_autotune",
-           "escort_plan_autotune_backward",
+           "escort_plan_autotune_backward", "escort_plan_copy_tuning",
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
-           "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_measure_fp32_peak",
+           "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
+           "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
            "escort_last_error", "escort_version"]
 
 lib.escort_last_error.restype = C.c_char_p

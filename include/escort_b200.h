@@ -169,6 +169,9 @@ ESCORT_API int escort_comm_destroy(void *comm);
 /* register-resident FFMA microbenchmark used for the FP32 roofline denominator;
  * returns achieved TFLOP/s in *tflops_host, SM count and SM clock (kHz, from device attributes). */
 ESCORT_API int escort_measure_fp32_peak(int variant, int iters, double *tflops_host, int *sm_count_host, int *clock_khz_host);
+/* diagnostics: the TMEM kernels bound every mbarrier wait (~2 s); a wait that gives up records {code, block, warp,
+ * barrier offset, parity, ...} in 16 host-mapped words before trapping.  Copies them to out16. */
+ESCORT_API int escort_tmem_debug(int *out16);
 ESCORT_API const char *escort_last_error(void);
 ESCORT_API const char *escort_version(void);
 

@@ -1,0 +1,314 @@
+"""GPU parity at the sizes and with the plans bench.py times ("untested configs"): full BASELINE layer
+shapes, plan.autotune() at the bench batch size (so the TMEM-window variants, layout_rank > 0 and the FFMA2 / 16-warp tile
+variants are all reachable), outputs of the tuned plan against the reference's own CPU kernels (oracle/_ref, or the C
+port) on an 8-image slice, forward and masked backward.  Plus: every TMEM variant on small odd geometries, the
+run-to-run bound of the atomically accumulated backward weight, refresh-then-retune, and the NCCL entry
+points on a real communicator."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _layer(capi, po, spec, idx, N=None):
+    from caffe_escoin_b200 import workloads as wl
+    torch = _torch()
+    if N is not None:
+        spec = spec._replace(N=N)
+    d = wl.make_layer_data(spec, idx)
+    geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
+    csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)
+    plan = capi.Plan(geom, csr)
+    return spec, d, plan
+
+
+def _ref_forward(po, spec, d, n, relu):
+    g = po.Geom(n, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+    ocsr = po.weight_align(d["w"], g)
+    if po.have_ref():
+        return po.ref_conv_forward(d["x"][:n], ocsr, g, d["bias"], relu=relu)[0], g
+    return po.conv_forward(d["x"][:n], ocsr, g, d["bias"], relu=relu), g
+
+
+def _named(net, name):
+    from caffe_escoin_b200 import workloads as wl
+    for i, s in enumerate(wl.NETWORKS[net]):
+        if s.name.endswith(name):
+            return s, i
+    raise KeyError(name)
+
+
+FULL = [("alexnet", "conv2", 256), ("alexnet", "conv4", 256), ("alexnet", "conv5", 256),
+        ("googlenet", "conv2_3x3", 128), ("googlenet", "inception_3b_5x5", 128), ("googlenet", "inception_5b_3x3", 128),
+        ("resnet50", "res2a_branch2b", 256), ("resnet50", "res5a_branch2b", 256)]
+
+
+@pytest.mark.parametrize("net,name,N", FULL, ids=lambda v: str(v))
+def test_full_size_autotuned_forward_and_backward(capi, po, net, name, N):
+    torch = _torch()
+    spec0, idx = _named(net, name)
+    spec, d, plan = _layer(capi, po, spec0, idx, N)
+    plan.autotune(N)
+    plan.autotune_backward(N)
+    fwd_kernel = plan.kernel_name
+    assert not fwd_kernel.endswith("generic"), "autotune fell back to the generic kernel: " + plan.describe()
+    x = torch.from_numpy(d["x"]).cuda()
+    b = torch.from_numpy(d["bias"]).cuda() if d["bias"] is not None else None
+    y = plan.forward(x, b, relu=True)
+    torch.cuda.synchronize()
+    n = 8
+    ref, _ = _ref_forward(po, spec, d, n, True)
+    assert po.rel_l2(y[:n].cpu().numpy(), ref) < TOL, plan.describe()
+    # the last images of the batch too (tile / unit tails)
+    refl, gl = _ref_forward(po, spec, {"w": d["w"], "x": d["x"][N - 2:], "bias": d["bias"]}, 2, True)
+    assert po.rel_l2(y[N - 2:].cpu().numpy(), refl) < TOL
+    # masked backward on a 2-image slice (the oracle's restatement: the reference's own backward is dense cuBLAS)
+    nb = 2
+    g2 = po.Geom(nb, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+    dy = np.random.default_rng(7).uniform(-1, 1, (nb,) + tuple(ref.shape[1:])).astype(np.float32)
+    wd = torch.zeros(d["w"].shape, device="cuda")
+    dyd = torch.from_numpy(dy).cuda()
+    plan.backward_weight(x[:nb].contiguous(), dyd, wd_dense=wd)
+    dx = plan.backward_data(dyd)
+    torch.cuda.synchronize()
+    wd_o, _, dx_o = po.conv_backward(d["x"][:nb], dy, d["w"], g2, mask_only=True, want_b=False)
+    assert po.rel_l2(wd.cpu().numpy(), wd_o) < TOL
+    assert po.rel_l2(dx.cpu().numpy(), dx_o) < TOL
+    # building the backward plans must not disturb the forward plan (r02 regression: the TMEM plan was dropped)
+    assert plan.kernel_name == fwd_kernel
+
+
+def _tm_variants(capi, plan):
+    out = []
+    for v in range(1, 120):
+        try:
+            plan.set_config(v, 0)
+        except capi.EscortError:
+            continue
+        if plan.kernel_name.startswith("sconv_tmem"):
+            out.append(v)
+    return out
+
+
+SMALL = [  # N, Cin, Cout, H, k, pad, dilation, group, sparsity, relu
+    (5, 32, 48, 13, 3, 1, 1, 1, 0.88, True),
+    (3, 16, 32, 27, 5, 2, 1, 2, 0.85, True),
+    (4, 20, 50, 12, 5, 0, 1, 1, 0.80, False),     # LeNet conv2: no padding
+    (2, 16, 16, 56, 3, 1, 1, 1, 0.70, False),
+    (9, 64, 40, 7, 3, 1, 1, 1, 0.70, True),
+    (3, 40, 24, 14, 1, 0, 1, 1, 0.60, True),      # 1x1
+    (2, 8, 70, 10, 3, 1, 1, 1, 0.0, False),       # dense weights, ragged channel blocks
+    (2, 300, 130, 6, 3, 1, 1, 1, 0.90, True),     # many chunks
+    (3, 12, 20, 14, 3, 2, 2, 1, 0.50, True),      # dilation 2 (reference sconv_dilation, math_functions.cu:154-179)
+    (1, 6, 10, 40, 3, 1, 1, 1, 0.50, False),      # padded row wider than 32: two loader column blocks
+    (2, 8, 8, 5, 3, 3, 1, 1, 0.30, False),        # pad > k-1: outputs beyond the padded pitch -> TMEM must refuse
+]
+
+
+@pytest.mark.parametrize("case", SMALL, ids=lambda c: "N%d_C%d_M%d_H%d_k%d_p%d_d%d_g%d_sp%g" % c[:9])
+def test_every_tmem_variant_vs_oracle(capi, po, case):
+    torch = _torch()
+    N, Cin, Cout, H, k, pad, dil, grp, sp, relu = case
+    rng = np.random.default_rng(N * 131 + Cin)
+    from caffe_escoin_b200 import workloads as wl
+    w = wl.prune_magnitude(rng.normal(0, 0.01, (Cout, Cin // grp, k, k)).astype(np.float32), sp)
+    x = rng.uniform(-1, 1, (N, Cin, H, H)).astype(np.float32)
+    bias = rng.normal(0, 0.1, Cout).astype(np.float32)
+    g = po.Geom(N, Cin, H, H, Cout, k, 1, pad, dil, grp)
+    ocsr = po.weight_align(w, g)
+    y_ref = po.conv_forward(x, ocsr, g, bias, relu=relu)
+    geom = capi.make_geom(Cin, Cout, H, H, k, 1, pad, dil, grp)
+    csr = capi.weight_align(torch.from_numpy(w).cuda(), geom)
+    plan = capi.Plan(geom, csr)
+    variants = _tm_variants(capi, plan)
+    if pad > (k - 1) * dil:
+        assert variants == [], "the flattened layout does not cover outputs beyond the padded pitch"
+        return
+    assert variants, "no TMEM variant applies to " + str(case)
+    xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(bias).cuda()
+    for v in variants:
+        plan.set_config(v, 0)
+        y = torch.full(y_ref.shape, float("nan"), device="cuda")
+        plan.forward(xd, bd, relu=relu, top=y)
+        torch.cuda.synchronize()
+        err = po.rel_l2(y.cpu().numpy(), y_ref)
+        assert err < TOL, "%s: rel_l2 %.3g  %s" % (plan.kernel_name, err, plan.describe())
+
+
+def test_tmem_forward_is_bit_identical_to_csr_order_accumulation(capi, po):
+    """Per output channel the TMEM kernel accumulates the nonzeros in CSR order with fp32 FMAs, like the reference's
+    sequential row walk (sconv.hpp:594-678): the C port of that loop, compiled without contraction differences, agrees
+    to the last bit on a layer whose products are exactly representable."""
+    torch = _torch()
+    rng = np.random.default_rng(5)
+    N, Cin, Cout, H, k = 3, 24, 40, 13, 3
+    from caffe_escoin_b200 import workloads as wl
+    w = wl.prune_magnitude(rng.integers(-8, 9, (Cout, Cin, k, k)).astype(np.float32), 0.8)
+    x = rng.integers(-16, 17, (N, Cin, H, H)).astype(np.float32)
+    g = po.Geom(N, Cin, H, H, Cout, k, 1, 1, 1, 1)
+    y_ref = po.conv_forward(x, po.weight_align(w, g), g, None, relu=False)
+    geom = capi.make_geom(Cin, Cout, H, H, k, 1, 1, 1, 1)
+    plan = capi.Plan(geom, capi.weight_align(torch.from_numpy(w).cuda(), geom))
+    for v in _tm_variants(capi, plan):
+        plan.set_config(v, 0)
+        y = plan.forward(torch.from_numpy(x).cuda(), None, relu=False)
+        assert np.array_equal(y.cpu().numpy(), y_ref), plan.kernel_name
+
+
+def test_backward_weight_run_to_run_bound(capi, po):
+    """The backward-weight kernel adds per-unit partial sums with atomics: the order varies from run to run, the result
+    must not (to 1e-5 relative L2), and must stay within tolerance of the oracle."""
+    torch = _torch()
+    spec0, idx = _named("alexnet", "conv3")
+    spec, d, plan = _layer(capi, po, spec0, idx, 32)
+    x = torch.from_numpy(d["x"]).cuda()
+    dy = torch.from_numpy(np.random.default_rng(3).uniform(-1, 1, (32, spec.Cout, plan.Ho, plan.Wo)).astype(np.float32)).cuda()
+    runs = []
+    for _ in range(3):
+        wd = torch.zeros(d["w"].shape, device="cuda")
+        plan.backward_weight(x, dy, wd_dense=wd)
+        torch.cuda.synchronize()
+        runs.append(wd.cpu().numpy())
+    assert po.rel_l2(runs[1], runs[0]) <= 1e-5 and po.rel_l2(runs[2], runs[0]) <= 1e-5
+
+
+def test_refresh_then_retune_keeps_the_refreshed_values(capi, po):
+    """escort_plan_set_config / autotune rebuild the streams from the create-time snapshot; after a refresh
+    they must carry the CURRENT values (forward and backward data), whichever kernel family the rebuild selects."""
+    torch = _torch()
+    spec0, idx = _named("alexnet", "conv3")
+    spec, d, plan = _layer(capi, po, spec0._replace(Cin=32, Cout=48), idx, 4)
+    g = po.Geom(4, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+    w2 = (d["w"] * np.float32(-1.75)).astype(np.float32)  # same mask, new values
+    ocsr2 = po.weight_align(w2, g)
+    y_ref = po.conv_forward(d["x"], ocsr2, g, None, relu=False)
+    x = torch.from_numpy(d["x"]).cuda()
+    plan.refresh_values(torch.from_numpy(w2).cuda())
+    dy = np.random.default_rng(11).uniform(-1, 1, y_ref.shape).astype(np.float32)
+    _, _, dx_ref = po.conv_backward(d["x"], dy, w2, g, mask_only=True, want_w=False, want_b=False)
+    seen = set()
+    for v in [-1, 0] + list(range(1, 120)):
+        try:
+            plan.set_config(v, 0)
+        except capi.EscortError:
+            continue
+        fam = plan.kernel_name.split("_")[1] if "_" in plan.kernel_name else plan.kernel_name
+        if (fam, v > 0) in seen and v > 12:
+            continue  # one representative per family is enough beyond the first dozen
+        seen.add((fam, v > 0))
+        y = plan.forward(x, None, relu=False)
+        torch.cuda.synchronize()
+        assert po.rel_l2(y.cpu().numpy(), y_ref) < TOL, "stale values after set_config(%d): %s" % (v, plan.kernel_name)
+    plan.autotune(4)
+    plan.autotune_backward(4)
+    y = plan.forward(x, None, relu=False)
+    dx = plan.backward_data(torch.from_numpy(dy).cuda())
+    torch.cuda.synchronize()
+    assert po.rel_l2(y.cpu().numpy(), y_ref) < TOL
+    assert po.rel_l2(dx.cpu().numpy(), dx_ref) < TOL
+
+
+def test_copy_tuning_reproduces_the_source_plan(capi, po):
+    torch = _torch()
+    spec0, idx = _named("resnet50", "res4a_branch2b")
+    spec, d, a = _layer(capi, po, spec0._replace(Cin=64, Cout=64), idx, 8)
+    _, d2, b = _layer(capi, po, spec0._replace(Cin=64, Cout=64), idx + 1, 8)
+    a.autotune(8)
+    a.autotune_backward(8)
+    b.copy_tuning(a)
+    assert b.kernel_names() == a.kernel_names()
+    ref, _ = _ref_forward(po, spec, d2, 8, False)
+    y = b.forward(torch.from_numpy(d2["x"]).cuda(), None, relu=False)
+    torch.cuda.synchronize()
+    assert po.rel_l2(y.cpu().numpy(), ref) < TOL
+
+
+def test_nccl_entries_on_a_real_communicator_single_rank(capi):
+    """escort_comm_* + escort_allreduce_grads / escort_broadcast with comm != NULL (that branch had never
+    executed): one rank, so the sum is the identity and the result is the scaled input."""
+    torch = _torch()
+    comm = capi.NcclComm(1, 0)
+    assert comm.handle
+    x = torch.arange(1000, dtype=torch.float32, device="cuda")
+    capi.allreduce_grads(x, 0.5, comm)
+    capi.broadcast(x, 0, comm)
+    part = x[3:503]  # an unaligned slice of a flat buffer (per-layer exchange)
+    capi.allreduce_grads(part, 2.0, comm)
+    torch.cuda.synchronize()
+    exp = np.arange(1000, dtype=np.float32) * 0.5
+    exp[3:503] *= 2.0
+    assert np.array_equal(x.cpu().numpy(), exp)
+    comm.destroy()
+
+
+def _nccl_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # only to ship the 128-byte id
+    from caffe_escoin_b200 import capi, workloads as wl
+    from oracle import pyoracle as po
+
+    def exchange_id(raw):
+        t = torch.tensor(list(raw) if raw is not None else [0] * 128, dtype=torch.uint8)
+        dist.broadcast(t, 0)
+        return bytes(t.tolist())
+    comm = capi.NcclComm(world, rank, exchange_id)
+    # a thin ResNet layer, batch 4 split over the ranks: exchanged CSR-ordered gradient == full-batch gradient / world
+    spec = wl.RESNET50[7]._replace(N=4, Cin=32, Cout=32)
+    d = wl.make_layer_data(spec, 7)
+    geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
+    w = torch.from_numpy(d["w"]).cuda()
+    capi.broadcast(w, 0, comm)
+    csr = capi.weight_align(w, geom)
+    plan = capi.Plan(geom, csr)
+    dy = np.random.default_rng(2).uniform(-1, 1, (4, spec.Cout, plan.Ho, plan.Wo)).astype(np.float32)
+    per = 4 // world
+    sl = slice(rank * per, (rank + 1) * per)
+    gsize = int(csr["rowptr"].cpu().numpy()[-1])
+    grad = torch.zeros((gsize + 3) // 4 * 4, device="cuda")
+    plan.backward_weight(torch.from_numpy(d["x"][sl]).cuda(), torch.from_numpy(dy[sl]).cuda(), wd_csr=grad[:gsize],
+                         accumulate=False)
+    capi.allreduce_grads(grad, 1.0 / world, comm)
+    torch.cuda.synchronize()
+    g4 = po.Geom(4, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+    wd_o, _, _ = po.conv_backward(d["x"], dy, d["w"], g4, mask_only=True, want_b=False, want_x=False)
+    ocsr = po.weight_align(d["w"], g4, stretch=False)
+    exp = wd_o.reshape(spec.Cout, -1)[np.repeat(np.arange(spec.Cout), np.diff(ocsr["rowptr"][:spec.Cout + 1])),
+                                      ocsr["colidx"][:gsize]] / world
+    err = po.rel_l2(grad[:gsize].cpu().numpy(), exp)
+    comm.destroy()
+    dist.destroy_process_group()
+    q.put((rank, err))
+
+
+def test_nccl_exchange_two_gpus_equals_full_batch_gradient(capi, po):
+    torch = _torch()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, err in res:
+        assert err < TOL, "rank %d: exchanged gradient differs from full-batch / world: %.3g" % (rank, err)

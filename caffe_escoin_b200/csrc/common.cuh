@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -27,6 +28,9 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
       return ESCORT_EINVAL;                       \
     }                                             \
   } while (0)
+
+// internal: the tile kernel cannot take this launch (e.g. a bottom pointer TMA cannot address): use the generic kernel
+#define ESCORT_ETRYGENERIC (-100)
 
 inline int out_dim(int in, int pad, int k, int s, int d) { return (in + 2 * pad - (d * (k - 1) + 1)) / s + 1; }
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -80,6 +84,9 @@ struct escort_plan {
   // ---- backward weight through the tile kernel's "W" variants (stride 1 only), built on first use
   escort::TilePlan *tile_w;
   int tile_w_tried;
+  // ---- knobs read ONCE at plan creation (never getenv on the launch path) and the lock of the lazy builds
+  int generic_backward;   // ESCORT_GENERIC_BACKWARD: keep the backward on the generic kernels (tests)
+  std::mutex *mu;         // guards the first-use builds of bwd / tile_w when several host threads share a plan
 };
 
 namespace escort {

@@ -381,6 +381,8 @@ extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, co
   p->variant = -1;
   p->layout_rank = 0;
   p->host_nz = nzs;
+  p->generic_backward = getenv("ESCORT_GENERIC_BACKWARD") ? 1 : 0;
+  p->mu = new std::mutex();
   cudaGetDevice(&p->device);
 
   const int H = g.height, W = g.width;
@@ -439,6 +441,7 @@ extern "C" int escort_plan_destroy(escort_plan *p) {
   if (p->tile_w) tile_plan_free(p->tile_w);
   if (p->bwd) escort_plan_destroy(p->bwd);
   delete p->host_nz;
+  delete p->mu;
   delete p;
   return 0;
 }
@@ -468,6 +471,7 @@ static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
     return 0;
   }
   q->device = p->device;
+  q->generic_backward = p->generic_backward;
   q->nnz = p->nnz;
   q->variant = -1;
   q->host_nz = new std::vector<Nz>();
@@ -622,6 +626,7 @@ static int autotune_one(escort_plan *p, int num, cudaStream_t stream) {
   cudaFree(x);
   cudaFree(y);
   cudaGetLastError();
+  if (first.empty() && !p->d_rowptr) return escort_plan_set_config(p, -1, 0);  // a backward sub-plan has no generic kernel: keep its default
   return escort_plan_set_config(p, best_v, best_rank);
 }
 
@@ -662,7 +667,8 @@ extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t str
 extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune_backward: bad arguments");
-  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+  std::lock_guard<std::mutex> lock(*p->mu);
+  if (!p->bwd && !p->bwd_tried && !p->generic_backward) {
     int rc = build_bwd_plan(p, stream);
     if (rc) return rc;
   }
@@ -670,7 +676,7 @@ extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_str
     int rc = autotune_one(p->bwd, num, stream);
     if (rc) return rc;
   }
-  if (getenv("ESCORT_GENERIC_BACKWARD") || getenv("ESCORT_BWDW_VARIANT")) return 0;
+  if (p->generic_backward || getenv("ESCORT_BWDW_VARIANT")) return 0;
   return tile_bwdw_autotune(p, num, stream);  // and the backward-weight (W) variant
 }
 
@@ -681,8 +687,11 @@ extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom
   if (num == 0) return 0;  // empty batch: nothing to do (pointers may be null)
   ESCORT_REQUIRE(bottom && top, "escort_sconv_forward: null tensor");
   if (p->tm && tmem_batch_fits(p, num)) return tmem_forward(p, num, bottom, bias, fuse_relu, top, stream);
-  if (p->tile) return tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
-  ESCORT_REQUIRE(p->d_rowptr, "escort_sconv_forward: batch too large for this plan");
+  if (p->tile) {
+    const int rc = tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
+    if (rc != ESCORT_ETRYGENERIC) return rc;
+  }
+  ESCORT_REQUIRE(p->d_rowptr, "escort_sconv_forward: this launch needs the generic kernel, which a backward sub-plan does not have");
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(p->Ho * p->Wo, kGenThreads), g.num_output, num);
   ESCORT_REQUIRE(num <= 65535, "escort_sconv_forward: batch too large for the generic kernel");
@@ -699,12 +708,19 @@ extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *
   ESCORT_REQUIRE(p && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
   if (num == 0) return 0;
   ESCORT_REQUIRE(top_diff && bottom_diff, "escort_sconv_backward_data: null tensor");
-  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
-    int rc = build_bwd_plan(p, stream);
-    if (rc) return rc;
+  if (!p->bwd && !p->bwd_tried && !p->generic_backward) {
+    std::lock_guard<std::mutex> lock(*p->mu);  // first use: one thread builds, the others find it built
+    if (!p->bwd && !p->bwd_tried) {
+      int rc = build_bwd_plan(p, stream);
+      if (rc) return rc;
+    }
   }
-  if (p->bwd && !getenv("ESCORT_GENERIC_BACKWARD") && (p->bwd->tile || (p->bwd->tm && tmem_batch_fits(p->bwd, num))))
-    return escort_sconv_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
+  if (p->bwd && !p->generic_backward && (p->bwd->tile || (p->bwd->tm && tmem_batch_fits(p->bwd, num)))) {
+    int rc = ESCORT_ETRYGENERIC;
+    if (p->bwd->tm && tmem_batch_fits(p->bwd, num)) rc = tmem_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
+    else if (p->bwd->tile) rc = tile_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
+    if (rc != ESCORT_ETRYGENERIC) return rc;
+  }
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
   sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
@@ -722,14 +738,19 @@ extern "C" int escort_sconv_backward_weight(escort_plan *p, int num, const float
   ESCORT_REQUIRE(weight_diff_dense || weight_diff_csr, "escort_sconv_backward_weight: no output buffer");
   if (num == 0 || p->nnz == 0) return 0;
   ESCORT_REQUIRE(bottom && top_diff, "escort_sconv_backward_weight: null tensor");
-  if (!p->tile_w && !p->tile_w_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
-    p->tile_w_tried = 1;
-    int rc = tile_bwdw_build(p, stream);
-    if (rc) return rc;
-    ESCORT_CUDA(cudaStreamSynchronize(stream));
+  if (!p->tile_w && !p->tile_w_tried && !p->generic_backward) {
+    std::lock_guard<std::mutex> lock(*p->mu);
+    if (!p->tile_w && !p->tile_w_tried) {
+      int rc = tile_bwdw_build(p, stream);
+      p->tile_w_tried = 1;
+      if (rc) return rc;
+      ESCORT_CUDA(cudaStreamSynchronize(stream));
+    }
   }
-  if (p->tile_w && !getenv("ESCORT_GENERIC_BACKWARD"))
-    return tile_bwdw(p, num, bottom, top_diff, weight_diff_dense, weight_diff_csr, accumulate, stream);
+  if (p->tile_w && !p->generic_backward) {
+    const int rc = tile_bwdw(p, num, bottom, top_diff, weight_diff_dense, weight_diff_csr, accumulate, stream);
+    if (rc != ESCORT_ETRYGENERIC) return rc;
+  }
   const escort_geom &g = p->g;
   const int warps = 8;
   const long blocks = (p->nnz + warps - 1) / warps;
@@ -761,10 +782,13 @@ extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense,
   ESCORT_LAUNCH_CHECK();
   refresh_t_kernel<<<blocks, 256, 0, stream>>>(p->nnz, p->d_meta, p->d_tsrc, p->d_tmeta);
   ESCORT_LAUNCH_CHECK();
-  if (!p->bwd && !p->bwd_tried && !getenv("ESCORT_GENERIC_BACKWARD")) {
+  if (!p->bwd && !p->bwd_tried && !p->generic_backward) {
     // a refresh means training: build the backward-data sub-plan now, so that it never starts from stale values
-    int rc = build_bwd_plan(p, stream);
-    if (rc) return rc;
+    std::lock_guard<std::mutex> lock(*p->mu);
+    if (!p->bwd && !p->bwd_tried) {
+      int rc = build_bwd_plan(p, stream);
+      if (rc) return rc;
+    }
   }
   if (p->bwd) {
     int rc = tile_refresh(p->bwd, weights_dense, stream);

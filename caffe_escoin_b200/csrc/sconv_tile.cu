@@ -52,15 +52,16 @@ struct VariantDesc {
 ESCORT_VARIANT_LIST(ESCORT_VARIANT_DECL)
 static constexpr int kNumVariants = ESCORT_NUM_VARIANTS;
 static const VariantDesc *variants() {
-  static VariantDesc tab[kNumVariants];
-  static bool init = false;
-  if (!init) {
+  // C++11 magic static: initialised once, thread safe (Caffe runs one host thread per GPU)
+  static const struct Table {
+    VariantDesc tab[kNumVariants];
+    Table() {
 #define ESCORT_VARIANT_FILL(ID, OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL) \
   tab[ID] = {OT, TY, TX, KH, KW, S, PAIR, NCW, NLW, NTW, MODE, SHFL, tile_variant_name_##ID(), tile_variant_kernel_##ID(), tile_variant_bench_##ID(), tile_variant_bwdw_##ID()};
-    ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
-    init = true;
-  }
-  return tab;
+      ESCORT_VARIANT_LIST(ESCORT_VARIANT_FILL)
+    }
+  } table;
+  return table.tab;
 }
 #define kVariants (variants())
 
@@ -184,22 +185,22 @@ int tile_bwdw_variant(const escort_plan *plan) {
 
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+static TmaEncodeFn resolve_tma_encoder() {
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  TmaEncodeFn fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    fn = (TmaEncodeFn)p;
+  cudaGetLastError();
+  return fn;
+}
 static TmaEncodeFn tma_encoder() {
-  static TmaEncodeFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = (TmaEncodeFn)p;
-    cudaGetLastError();
-  }
+  static const TmaEncodeFn fn = resolve_tma_encoder();  // magic static: resolved once, thread safe
   return fn;
 }
 
-static thread_local bool g_building_w = false;
+static thread_local bool g_building_w = false;  // set while tile_bwdw_build runs tile_plan_build for a W variant
 
 namespace {
 struct Layout {
@@ -278,7 +279,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   // B200) -- the innermost start coordinate must keep the global address 16-byte aligned, hence the aligned-body
   // layout for TMA and the cp.async loader for patch-aligned rows
   const bool use_tma_b = false;
-  const bool use_tma = (tma_ok && !plan_b_variant) || use_tma_b;
+  const bool use_tma = (tma_ok && !plan_b_variant) || use_tma_b;  // (box limits are checked once the tiling is known)
   if ((V.MODE == 1 || V.MODE == 3 || V.MODE == 5) && !use_tma) return 0;
   // aligned body (PAIR 1, TMA): data column 0 sits on a 16-byte boundary, HL = 4 halo columns to its left and the
   // lane base is the tile's first output column; patch aligned: the halo is exactly pad_w positions wide and the lane
@@ -361,6 +362,7 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   std::stable_sort(cands.begin(), cands.end(), [](const Layout &a, const Layout &b) { return a.score > b.score; });
   if (layout_rank < 0 || layout_rank >= (int)cands.size()) return 0;
   const Layout best = cands[layout_rank];  // rank 0 = the heuristic's favourite; autotune also times the runners-up
+  if (use_tma && (best.P > 256 || best.R > 256)) return 0;  // cuTensorMapEncodeTiled: boxDim <= 256 (CI is capped at 32 below)
   const int WP = best.WP, G = best.G, GP = G / PAIR, BR = best.BR, P = best.P, R = best.R;
   const int WO = NCW / WP;
   const int nbands = ceil_div(PY, BR);
@@ -677,6 +679,32 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   return 0;
 }
 
+// Tensor map of `bottom` as a 4-D tensor {W, H, C, N}; one box = the band's R rows x P columns of CI channels of one image,
+// starting at x = -HL (out-of-bounds elements read as zero: the halo costs nothing).  Cached per (pointer, batch).
+// Returns 1 if the pointer cannot be used with TMA (misaligned): the caller falls back to the generic kernel.
+static int tile_tensor_map(TilePlan *tp, const TileParams &prm, const float *bottom, int num, CUtensorMap *out) {
+  if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) return 1;
+  if (tp->tmap_ptr == bottom && tp->tmap_num == num) {
+    *out = tp->tmap;
+    return 0;
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)prm.W, (cuuint64_t)prm.H, (cuuint64_t)prm.C, (cuuint64_t)num};
+  const cuuint64_t strides[3] = {(cuuint64_t)prm.W * 4, (cuuint64_t)prm.H * prm.W * 4, (cuuint64_t)prm.C * prm.H * prm.W * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)prm.P, (cuuint32_t)prm.R, (cuuint32_t)prm.CI, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  CUresult r = tma_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(bottom), dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return ESCORT_EINVAL;
+  }
+  tp->tmap = *out;
+  tp->tmap_ptr = bottom;
+  tp->tmap_num = num;
+  return 0;
+}
+
 int tile_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,
                  cudaStream_t stream) {
   TilePlan *tp = plan->tile;
@@ -688,24 +716,9 @@ int tile_forward(escort_plan *plan, int num, const float *bottom, const float *b
   CUtensorMap tmap;
   memset(&tmap, 0, sizeof(tmap));
   if (prm.use_tma) {
-    // bottom as a 4-D tensor {W, H, C, N}; one box = the band's R rows x P columns of CI channels of one image,
-    // starting at x = -pad_w (out-of-bounds elements read as zero: the halo costs nothing)
-    if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) {
-      set_last_error("escort_sconv_forward: bottom must be 16-byte aligned for the TMA-staged kernel");
-      return ESCORT_EINVAL;
-    }
-    const cuuint64_t dims[4] = {(cuuint64_t)prm.W, (cuuint64_t)prm.H, (cuuint64_t)prm.C, (cuuint64_t)num};
-    const cuuint64_t strides[3] = {(cuuint64_t)prm.W * 4, (cuuint64_t)prm.H * prm.W * 4,
-                                   (cuuint64_t)prm.C * prm.H * prm.W * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)prm.P, (cuuint32_t)prm.R, (cuuint32_t)prm.CI, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(bottom), dims, strides, box,
-                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_last_error("escort_sconv_forward: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-      return ESCORT_EINVAL;
-    }
+    const int rc = tile_tensor_map(tp, prm, bottom, num, &tmap);
+    if (rc == 1) return ESCORT_ETRYGENERIC;  // misaligned bottom: this launch goes to the generic kernel
+    if (rc) return rc;
   }
   void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&bias, (void *)&fuse_relu, (void *)&top,
                   (void *)&nunits, (void *)&tmap};
@@ -735,30 +748,17 @@ int tile_bwdw(escort_plan *plan, int num, const float *bottom, const float *top_
   int nunits = (int)((size_t)prm.n_igroups * prm.nbands * prm.ngroups * prm.ogroups);
   const unsigned grid = (unsigned)std::min(nunits, tp->num_sms);
   const VariantDesc &V = kVariants[tp->vidx];
+  CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  if (prm.use_tma) {
+    const int rc = tile_tensor_map(tp, prm, bottom, num, &tmap);
+    if (rc == 1) return ESCORT_ETRYGENERIC;
+    if (rc) return rc;
+  }
   if (!accumulate && wd_csr) {  // the dense diff always accumulates (Caffe's contract); the CSR-ordered copy may be overwritten
     const unsigned blocks = (unsigned)((plan->nnz + 255) / 256);
     zero_at_kernel<<<blocks, 256, 0, stream>>>(plan->nnz, plan->d_csr_pos, wd_csr);
     ESCORT_LAUNCH_CHECK();
-  }
-  CUtensorMap tmap;
-  memset(&tmap, 0, sizeof(tmap));
-  if (prm.use_tma) {
-    if ((reinterpret_cast<uintptr_t>(bottom) & 15) != 0) {
-      set_last_error("escort_sconv_backward_weight: bottom must be 16-byte aligned for the TMA-staged kernel");
-      return ESCORT_EINVAL;
-    }
-    const cuuint64_t dims[4] = {(cuuint64_t)prm.W, (cuuint64_t)prm.H, (cuuint64_t)prm.C, (cuuint64_t)num};
-    const cuuint64_t strides[3] = {(cuuint64_t)prm.W * 4, (cuuint64_t)prm.H * prm.W * 4,
-                                   (cuuint64_t)prm.C * prm.H * prm.W * 4};
-    const cuuint32_t box[4] = {(cuuint32_t)prm.P, (cuuint32_t)prm.R, (cuuint32_t)prm.CI, 1u};
-    const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
-    CUresult r = tma_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(bottom), dims, strides, box,
-                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-      set_last_error("escort_sconv_backward_weight: cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
-      return ESCORT_EINVAL;
-    }
   }
   void *args[] = {(void *)&prm, (void *)&num, (void *)&bottom, (void *)&top_diff, (void *)&wd_dense, (void *)&wd_csr,
                   (void *)&nunits, (void *)&tmap};
@@ -790,12 +790,19 @@ int tile_bwdw_build(escort_plan *plan, cudaStream_t stream, int variant) {
     // per-tap destinations (stream order), so that the flush needs one index load per tap instead of two dependent ones
     TilePlan *tp = plan->tile_w;
     const long n = plan->nnz;
-    ESCORT_CUDA(cudaMalloc((void **)&tp->d_tap_dense, std::max<long>(n, 1) * sizeof(int)));
-    ESCORT_CUDA(cudaMalloc((void **)&tp->d_tap_csr, std::max<long>(n, 1) * sizeof(int)));
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_dense_idx, tp->d_tap_dense);
-    gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_csr_pos, tp->d_tap_csr);
-    ESCORT_LAUNCH_CHECK();
+    cudaError_t e = cudaMalloc((void **)&tp->d_tap_dense, std::max<long>(n, 1) * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&tp->d_tap_csr, std::max<long>(n, 1) * sizeof(int));
+    if (e == cudaSuccess) {
+      const unsigned blocks = (unsigned)((n + 255) / 256);
+      gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_dense_idx, tp->d_tap_dense);
+      gather_idx_kernel<<<blocks, 256, 0, stream>>>(n, tp->d_tapidx, plan->d_csr_pos, tp->d_tap_csr);
+      e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) {  // never leave a half-built W plan behind: the generic kernel takes over
+      tile_plan_free(plan->tile_w);
+      plan->tile_w = nullptr;
+      return cuda_fail(e, "tile_bwdw_build", __FILE__, __LINE__);
+    }
   }
   return rc;
 }

@@ -63,6 +63,11 @@ struct TilePlan {
   int *d_tap_dense, *d_tap_csr;  // W variants: stream-order tap -> destination in the dense / CSR-ordered gradient
   size_t nrecords;
   int num_sms;
+  // the bulk-tensor map of the last (bottom pointer, batch) this plan was launched with: encoded on the host once per
+  // pair, not per launch (Caffe's blobs keep their addresses between iterations)
+  CUtensorMap tmap;
+  const void *tmap_ptr;
+  int tmap_num;
 };
 #endif
 

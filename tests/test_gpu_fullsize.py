@@ -312,3 +312,30 @@ def test_nccl_exchange_two_gpus_equals_full_batch_gradient(capi, po):
         p.join(timeout=60)
     for rank, err in res:
         assert err < TOL, "rank %d: exchanged gradient differs from full-batch / world: %.3g" % (rank, err)
+
+
+def test_misaligned_bottom_falls_back_instead_of_failing(capi, po):
+    """A TMA-staged tile plan cannot address a bottom pointer that is not 16-byte aligned (a Caffe blob view can be):
+    the launch must fall back to the generic kernel (it returned ESCORT_EINVAL), with the same result."""
+    torch = _torch()
+    spec0, idx = _named("resnet50", "res3a_branch2b")
+    spec, d, plan = _layer(capi, po, spec0._replace(Cin=16, Cout=16), idx, 2)
+    tma_v = None
+    for v in range(1, 60):
+        try:
+            plan.set_config(v, 0)
+        except capi.EscortError:
+            continue
+        if " tma " in plan.describe():
+            tma_v = v
+            break
+    if tma_v is None:
+        pytest.skip("no TMA-staged tile variant applies")
+    ref, _ = _ref_forward(po, spec, d, 2, False)
+    buf = torch.zeros(d["x"].size + 8, device="cuda")
+    xm = buf[1:1 + d["x"].size].view(d["x"].shape)       # 4 bytes off a 16-byte boundary
+    xm.copy_(torch.from_numpy(d["x"]).cuda())
+    assert xm.data_ptr() % 16 != 0
+    y = plan.forward(xm, None, relu=False)
+    torch.cuda.synchronize()
+    assert po.rel_l2(y.cpu().numpy(), ref) < TOL

@@ -22,27 +22,27 @@
 namespace escort {
 
 struct TmVariant {
-  int T, OT, NCW, NPW, CREGS, PREGS;
+  int T, OT, NCW, NPW, CREGS, PREGS, LC;
   const char *name;
   const void *kernel;
 };
 
 // (T positions per lane, OT output channels per compute warp, NCW compute warps, NPW producer warps, compute /
-// producer registers).  The setmaxnreg split must stay inside the CTA's own register pool:
-// NCW * (CREGS - R0) <= NPW * (R0 - PREGS) with R0 = the launch allocation (static_assert in the kernel)
-#define ESCORT_TM_VARIANTS(X)  \
-  X(16, 4, 16, 4, 104, 64)     \
-  X(32, 2, 16, 4, 104, 64)     \
-  X(16, 6, 12, 4, 144, 72)     \
-  X(32, 3, 12, 4, 144, 72)     \
-  X(16, 8, 8, 4, 216, 72)      \
-  X(32, 4, 8, 4, 216, 72)      \
-  X(16, 5, 12, 8, 128, 48)     \
-  X(16, 8, 8, 8, 192, 64)      \
-  X(32, 4, 8, 8, 192, 64)
+// producer registers, LC: 1 = the compute warps run the global -> shared loader, 0 = the producer warps do).  The
+// setmaxnreg split must stay inside the CTA's own register pool: NCW * (CREGS - R0) <= NPW * (R0 - PREGS) with R0 = the
+// launch allocation (static_assert in the kernel).  New variants go at the END: ids are cached by hosts.
+#define ESCORT_TM_VARIANTS(X)    \
+  X(16, 4, 16, 4, 104, 64, 0)    \
+  X(32, 2, 16, 4, 104, 64, 0)    \
+  X(16, 6, 12, 4, 144, 72, 0)    \
+  X(32, 3, 12, 4, 144, 72, 0)    \
+  X(16, 8, 8, 4, 216, 72, 0)     \
+  X(32, 4, 8, 4, 216, 72, 0)     \
+  X(32, 4, 8, 8, 192, 64, 0)     \
+  X(16, 4, 16, 4, 104, 64, 1)
 
-#define ESCORT_TM_ROW(T, OT, NCW, NPW, CR, PR) \
-  {T, OT, NCW, NPW, CR, PR, "sconv_tmem_t" #T "_o" #OT "_w" #NCW "p" #NPW, (const void *)&sconv_tmem_kernel<T, OT, NCW, NPW, CR, PR>},
+#define ESCORT_TM_ROW(T, OT, NCW, NPW, CR, PR, LC) \
+  {T, OT, NCW, NPW, CR, PR, LC, "sconv_tmem_t" #T "_o" #OT "_w" #NCW "p" #NPW "l" #LC, (const void *)&sconv_tmem_kernel<T, OT, NCW, NPW, CR, PR, LC>},
 static const TmVariant kTmVariants[] = {ESCORT_TM_VARIANTS(ESCORT_TM_ROW)};
 static constexpr int kNumTmVariants = (int)(sizeof(kTmVariants) / sizeof(kTmVariants[0]));
 
@@ -124,9 +124,9 @@ int tmem_choose_variant(const escort_plan *plan) {
   const int Cg = g.channels / g.group;
   const double density = (double)plan->nnz / ((double)g.num_output * Cg * g.kernel_h * g.kernel_w);
   // measured on B200 (profiles/r02_tmem_variant_sweep.txt): few taps per staged window (AlexNet 3x3 at 12 %: about one
-  // per output channel and input channel) -> fewer, fatter compute warps (8 output channels each); otherwise 16 warps
+  // per output channel and input channel) -> the compute warps wait for windows anyway and take over the loader
   const double taps_per_window = density * g.kernel_h * g.kernel_w;
-  const int prefs[2] = {taps_per_window < 1.6 ? 4 : 0, 0};
+  const int prefs[2] = {taps_per_window < 1.6 ? 7 : 0, 0};
   for (int tv : prefs)
     if (tmem_variant_applies(plan, tv)) return tv;
   for (int tv = 0; tv < kNumTmVariants; ++tv)

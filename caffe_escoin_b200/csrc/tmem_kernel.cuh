@@ -212,10 +212,82 @@ __device__ __forceinline__ TmUnit tm_decode_unit(const TmParams &p, int u) {
   return c;
 }
 
-// ---- producer warps (one per TMEM lane quadrant): global -> shared (cp.async, zero-filled halo) -> TMEM windows -----
+// ---- loader (run by the NL compute warps, each a share of the table steps): one chunk global -> shared memory --------
+// 4-byte cp.async driven by a per-unit table; halo positions and images past the batch are zero-filled (src size 0).
+struct TmLoadState {
+  int tab_unit;  // unit the table in shared memory was built for
+};
+template <int NL, int BAR>
+__device__ __forceinline__ void tm_issue_load(const TmParams &p, int num, const float *__restrict__ bottom, unsigned char *smem_raw,
+                                              unsigned smem_base, TmLoadState &ls, int it, int lw, int lane) {
+  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
+  int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
+  const int HW = p.H * p.W;
+  const int ui = it / p.nchunks, c = it - ui * p.nchunks;
+  const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
+  const int s = it % p.NS;
+  if (ui != ls.tab_unit) {
+    // per-unit loader table: entry (step j, lane) = {source element offset of the position inside channel 0's batch
+    // (-1: zero fill), skewed destination byte offset inside a staged channel row (-1: outside the staged range)}.
+    // A step = RO padded rows x LPR columns (or one 32-column block of a wide row).
+    ls.tab_unit = ui;
+    asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");  // every loader warp is done with the previous unit's table
+    const int tile_start = uc.tile * p.TILE;
+    const int R0 = tile_start / p.PW;
+    const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
+    const int nxb = (p.PW + 31) >> 5;
+    const int lpr = 1 << p.lpr_shift;
+    for (int e = lw * 32 + lane; e < p.ltab_n * 32; e += NL * 32) {
+      const int j = e >> 5, l = e & 31;
+      const int jr = j / nxb, xb = j - jr * nxb;
+      const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
+      int2 ent = make_int2(-1, -1);
+      if (row < nrows && x < p.PW) {
+        const int R = R0 + row;
+        const int d = R * p.PW + x - tile_start;
+        if (d >= 0 && d < p.SW) {
+          const int n = R / p.IMGR, yy = R - n * p.IMGR;
+          ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
+          if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = (n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w);
+        }
+      }
+      ltab[e] = ent;
+    }
+    asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");
+  }
+  if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
+  const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
+  const int nch = min(p.CI, p.Cg - c * p.CI);
+  const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
+  const unsigned row_bytes = (unsigned)p.SWP * 4u;
+  for (int j = lw; j < p.ltab_n; j += NL) {  // this warp's table steps, all channels of the chunk
+    const int2 e = ltab[j * 32 + lane];
+    if (e.y >= 0) {
+      const float *src = e.x >= 0 ? src0 + e.x : bottom;
+      const unsigned nbytes = e.x >= 0 ? 4u : 0u;
+      const size_t sstep = e.x >= 0 ? (size_t)HW : 0;
+      unsigned dst = stage_addr + (unsigned)e.y;
+#pragma unroll 2
+      for (int ch = 0; ch < nch; ++ch) {
+        tm_cp_async4(dst, src, nbytes);
+        src += sstep;
+        dst += row_bytes;
+      }
+    }
+  }
+  {  // record region of this (pass, chunk): contiguous 16-byte async copies
+    const int2 r = p.rtab[((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks + c];
+    const uint4 *src = p.prog + r.x;
+    const unsigned dst = stage_addr + p.in_bytes;
+    for (int i = lw * 32 + lane; i < r.y; i += NL * 32) tm_cp_async16(dst + 16u * i, src + i);
+  }
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
+}
+
+// ---- producer warps (NPW / 4 per TMEM lane quadrant): shared memory -> TMEM windows ------------------------------------
 // NPW producer warps = NPW / 4 per quadrant; pw = producer warp index, quadrant = pw % 4, pa = pw / 4 = which share of a
 // slot group's 16-column blocks this warp fills.
-template <int T, int NCW, int NPW, int FB>
+template <int T, int NCW, int NPW, int FB, int LC>
 __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, const float *__restrict__ bottom, int nunits,
                                                  unsigned char *smem_raw, unsigned smem_base, uint32_t tbase, int pw, int lane) {
   constexpr int NPQ = NPW / 4;
@@ -226,81 +298,18 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
   const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
   const int my_units = blockIdx.x < (unsigned)nunits ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
   const int total = my_units * p.nchunks;
-  const int LA = p.NS - 2;  // chunks the loads run ahead of the fills (the stage being refilled was released a whole chunk ago, so a load never waits for the chunk the compute warps are on)
-  const int HW = p.H * p.W;
-  int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
   unsigned slot = 0, round = 0;  // TMEM ring position of the next slot group to fill
   unsigned gsel = 0;             // slot groups seen so far (which producer of the quadrant fills the next one)
   const int nblocks = p.SLOTW >> 4;  // 16-column blocks per channel window
-  int tab_unit = -1;
 
-  auto issue_load = [&](int it) {
-    const int ui = it / p.nchunks, c = it - ui * p.nchunks;
-    const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
-    const int s = it % p.NS;
-    if (ui != tab_unit) {
-      // per-unit loader table, built by the four producer warps: entry (step j, lane) = {source element offset of the
-      // position inside channel 0's batch (-1: zero fill), skewed destination byte offset inside a staged channel
-      // row (-1: outside the staged range)}.  A step = RO padded rows x LPR columns (or one 32-column block of a wide row).
-      tab_unit = ui;
-      asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");  // every producer warp is done with the previous unit's table
-      const int tile_start = uc.tile * p.TILE;
-      const int R0 = tile_start / p.PW;
-      const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
-      const int nxb = (p.PW + 31) >> 5;
-      const int lpr = 1 << p.lpr_shift;
-      for (int e = pw * 32 + lane; e < p.ltab_n * 32; e += NPW * 32) {
-        const int j = e >> 5, l = e & 31;
-        const int jr = j / nxb, xb = j - jr * nxb;
-        const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
-        int2 ent = make_int2(-1, -1);
-        if (row < nrows && x < p.PW) {
-          const int R = R0 + row;
-          const int d = R * p.PW + x - tile_start;
-          if (d >= 0 && d < p.SW) {
-            const int n = R / p.IMGR, yy = R - n * p.IMGR;
-            ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
-            if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = (n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w);
-          }
-        }
-        ltab[e] = ent;
-      }
-      asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");
-    }
-    if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
-    const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
-    const int nch = min(p.CI, p.Cg - c * p.CI);
-    const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
-    const unsigned row_bytes = (unsigned)p.SWP * 4u;
-    for (int j = pw; j < p.ltab_n; j += NPW) {  // this warp's table steps, all channels of the chunk
-      const int2 e = ltab[j * 32 + lane];
-      if (e.y >= 0) {
-        const float *src = e.x >= 0 ? src0 + e.x : bottom;
-        const unsigned nbytes = e.x >= 0 ? 4u : 0u;
-        const size_t sstep = e.x >= 0 ? (size_t)HW : 0;
-        unsigned dst = stage_addr + (unsigned)e.y;
-#pragma unroll 4
-        for (int ch = 0; ch < nch; ++ch) {
-          tm_cp_async4(dst, src, nbytes);
-          src += sstep;
-          dst += row_bytes;
-        }
-      }
-    }
-    {  // record region of this (pass, chunk): contiguous 16-byte async copies
-      const int2 r = p.rtab[((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks + c];
-      const uint4 *src = p.prog + r.x;
-      const unsigned dst = stage_addr + p.in_bytes;
-      for (int i = pw * 32 + lane; i < r.y; i += NPW * 32) tm_cp_async16(dst + 16u * i, src + i);
-    }
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
-  };
-
-  for (int it = 0; it < LA && it < total; ++it) issue_load(it);
   // lane's first chunk of a window (before the skew): lane * T/4; a 16-column block never straddles a pad chunk
   const unsigned lane_chunk = (unsigned)lane * (T / 4);
+  TmLoadState ls = {-1};
+  const int LA = p.NS - 2;  // chunks the loads run ahead: the stage being refilled was released a whole chunk ago
+  if (!LC)
+    for (int it = 0; it < LA && it < total; ++it) tm_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, it, pw, lane);
   for (int it = 0; it < total; ++it) {
-    if (it + LA < total) issue_load(it + LA);
+    if (!LC && it + LA < total) tm_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, it + LA, pw, lane);
     const int s = it % p.NS;
     tm_mbar_wait(smem_full + 8 * s, (unsigned)((it / p.NS) & 1), 2, p.dbg);
     const int c = it % p.nchunks;
@@ -361,7 +370,7 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
 
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // warps 0 .. NCW-1: compute (TMEM lane quadrant = wid % 4, channel block = wid); warps NCW .. NCW+NPW-1: producers.
-template <int T, int OT, int NCW, int NPW, int CREGS, int PREGS>
+template <int T, int OT, int NCW, int NPW, int CREGS, int PREGS, int LC>
 __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
     sconv_tmem_kernel(const TmParams p, int num, const float *__restrict__ bottom, const float *__restrict__ bias, int fuse_relu,
                       float *__restrict__ top, int nunits) {
@@ -380,7 +389,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
 
   if (tid == 0) {
     for (int s = 0; s < p.NS; ++s) {
-      tm_mbar_init(smem_full + 8 * s, NPW * 32);     // every producer thread arrives through its cp.asyncs
+      tm_mbar_init(smem_full + 8 * s, (LC ? NCW : NPW) * 32);  // every loader thread arrives through its cp.asyncs
       tm_mbar_init(smem_empty + 8 * s, NCW + NPW);   // every warp releases the stage
     }
     for (int qq = 0; qq < 4; ++qq)
@@ -401,7 +410,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
 
   if (wid >= NCW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS) : "memory");
-    tm_producer_loop<T, NCW, NPW, (PREGS >= 72 ? 3 : PREGS >= 64 ? 2 : 1)>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
+    tm_producer_loop<T, NCW, NPW, (PREGS >= 72 ? 3 : PREGS >= 64 ? 2 : 1), LC>(p, num, bottom, nunits, smem_raw, smem_base, tbase, wid - NCW, lane);
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS) : "memory");
     const int q = wid & 3;
@@ -411,6 +420,13 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
     unsigned long long acc[OT][T / 2];
     unsigned st = 0, ph = 0;          // shared-memory stage ring
     unsigned slot = 0, sph = 0;       // TMEM slot ring
+    // LC: the compute warps are also the loader (at low weight density they idle on the producers, which never idle)
+    const int my_units = blockIdx.x < (unsigned)nunits ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int total = my_units * p.nchunks;
+    const int LA = p.NS - 2;  // chunks the loads run ahead: the stage being refilled was released a whole chunk ago
+    TmLoadState ls = {-1};
+    int kload = 0;
+    for (; LC && kload < LA && kload < total; ++kload) tm_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, kload, wid, lane);
 #pragma unroll 1
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
 #pragma unroll
@@ -419,6 +435,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
         for (int k = 0; k < T / 2; ++k) acc[o][k] = 0ull;
 #pragma unroll 1
       for (int c = 0; c < p.nchunks; ++c) {
+        if (LC && kload < total) {
+          tm_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, kload, wid, lane);
+          ++kload;
+        }
         tm_mbar_wait(smem_full + 8 * st, ph, 4, p.dbg);
         const unsigned region = smem_base + p.stage0_off + st * p.stage_bytes + p.in_bytes;
         unsigned rp;  // this warp's records (8 bytes each: {TMEM column inside the slot group, fp32 weight})

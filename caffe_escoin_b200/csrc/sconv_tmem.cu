@@ -18,11 +18,13 @@
 
 #include "common.cuh"
 #include "tmem_kernel.cuh"
+#include "tmem2_kernel.cuh"
 
 namespace escort {
 
 struct TmVariant {
   int T, OT, NCW, NPW, CREGS, PREGS, LC;
+  int kind;  // 0: producer warps fill the windows (sconv_tmem_kernel), 1: the compute warps do (sconv_tmem2_kernel)
   const char *name;
   const void *kernel;
 };
@@ -42,8 +44,15 @@ struct TmVariant {
   X(16, 4, 16, 4, 104, 64, 1)
 
 #define ESCORT_TM_ROW(T, OT, NCW, NPW, CR, PR, LC) \
-  {T, OT, NCW, NPW, CR, PR, LC, "sconv_tmem_t" #T "_o" #OT "_w" #NCW "p" #NPW "l" #LC, (const void *)&sconv_tmem_kernel<T, OT, NCW, NPW, CR, PR, LC>},
-static const TmVariant kTmVariants[] = {ESCORT_TM_VARIANTS(ESCORT_TM_ROW)};
+  {T, OT, NCW, NPW, CR, PR, LC, 0, "sconv_tmem_t" #T "_o" #OT "_w" #NCW "p" #NPW "l" #LC, (const void *)&sconv_tmem_kernel<T, OT, NCW, NPW, CR, PR, LC>},
+// self-fill kernels: (T, OT, NCW); no producer warps, the compute warps load and fill
+#define ESCORT_TM2_VARIANTS(X) \
+  X(16, 4, 16)                 \
+  X(16, 6, 12)                 \
+  X(16, 4, 12)                 \
+  X(16, 3, 16)
+#define ESCORT_TM2_ROW(T, OT, NCW) {T, OT, NCW, 0, 0, 0, 1, 1, "sconv_tmem2_t" #T "_o" #OT "_w" #NCW, (const void *)&sconv_tmem2_kernel<T, OT, NCW>},
+static const TmVariant kTmVariants[] = {ESCORT_TM_VARIANTS(ESCORT_TM_ROW) ESCORT_TM2_VARIANTS(ESCORT_TM2_ROW)};
 static constexpr int kNumTmVariants = (int)(sizeof(kTmVariants) / sizeof(kTmVariants[0]));
 
 struct TmemPlan {
@@ -89,6 +98,18 @@ extern "C" ESCORT_API int escort_tmem_debug(int *out16) {
   memcpy(out16, h, 64);
   return 0;
 }
+
+#ifdef ESCORT_TM_TRACE
+// trace build only (make TMTRACE=1): copies CTA 0's event log out and resets it; words = warps * events
+extern "C" ESCORT_API int escort_tmem_trace(unsigned long long *out, int *counts) {
+  ESCORT_CUDA(cudaDeviceSynchronize());
+  ESCORT_CUDA(cudaMemcpyFromSymbol(out, g_tm_trace, sizeof(unsigned long long) * kTmTraceWarps * kTmTraceEvents));
+  ESCORT_CUDA(cudaMemcpyFromSymbol(counts, g_tm_trace_n, sizeof(int) * kTmTraceWarps));
+  static int zeros[kTmTraceWarps];
+  ESCORT_CUDA(cudaMemcpyToSymbol(g_tm_trace_n, zeros, sizeof(zeros)));
+  return 0;
+}
+#endif
 
 int tmem_num_variants() { return kNumTmVariants; }
 const char *tmem_kernel_name(const TmemPlan *tp) { return tp->name; }
@@ -146,9 +167,10 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   const int HALO = (KH - 1) * g.dilation_h * PW + (KW - 1) * g.dilation_w;
   const int SLOTW = round_up(T + HALO, 16);
   int CHS = std::max(1, std::min(4, 512 / (3 * SLOTW)));  // three slot groups in flight; larger groups = fewer hand-shakes per tap
+  if (V.kind == 1) CHS = std::max(1, std::min(8, 256 / SLOTW));  // two buffers of 256 columns; one barrier per slot group
   if (const char *e = getenv("ESCORT_TM_CHS")) CHS = std::max(1, std::min(atoi(e), 512 / (2 * SLOTW)));  // tuning knob
   while (CHS > 1 && CHS * KH * KW > 255) --CHS;
-  const int NSLOT = std::min(512 / (CHS * SLOTW), kTmMaxSlots);
+  const int NSLOT = V.kind == 1 ? 2 : std::min(512 / (CHS * SLOTW), kTmMaxSlots);
   if (NSLOT < 2) return 0;
   const int TILE = 32 * T;
   const int SW = round_up(TILE - T + SLOTW, 32);
@@ -219,6 +241,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
       r.o = oc_slot[z.oc];
       r.ic = icl; r.kh = z.kh; r.kw = z.kw;
       r.col = (unsigned)((in_chunk % CHS) * SLOTW + z.kh * g.dilation_h * PW + z.kw * g.dilation_w);
+      if (V.kind == 1) r.col |= (unsigned)((w & 3) * 32) << 16;  // absolute TMEM address: the warp's lane quadrant, buffer 0
       r.val = z.val;
       r.src = (int)j;
       buckets[(((size_t)gi * ogroups + og) * nchunks + c) * NCW + w].push_back(r);
@@ -250,6 +273,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
               words.push_back(__builtin_bit_cast(unsigned, r.val));
             }
           }
+          if (V.kind == 1) words.resize(words.size() + 8, 0u);  // the record walk prefetches up to 32 bytes past the last record
           while (words.size() % 4) words.push_back(0u);
           const int len16 = (int)((words.size() - region_start) / 4);
           rtab[((size_t)gi * ogroups + og) * nchunks + c] = make_int2((int)(region_start / 4), len16);
@@ -257,7 +281,9 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
         }
     stage_bytes = in_bytes + round_up(max_region16 * 16, 128);
     NS = (int)std::min<long>(budget / stage_bytes, (long)kTmMaxStages);
-    if (NS >= 4 || (NS >= 3 && CI == CHS)) break;
+    // self-fill kernel: three larger stages (loads run one chunk ahead) beat four smaller ones by 2-3 % (fewer chunks)
+    const int ns_min = getenv("ESCORT_TM_NSMIN") ? atoi(getenv("ESCORT_TM_NSMIN")) : (V.kind == 1 ? 3 : 4);  // tuning knob
+    if (NS >= ns_min || (NS >= 3 && CI == CHS)) break;
     if (CI == CHS) return 0;  // does not fit
     CI = std::max(CHS, (CI * 3 / 4) / CHS * CHS);
   }
@@ -299,6 +325,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   }
   pr.oc_list = tp->d_oc_list; pr.prog = tp->d_prog; pr.rtab = tp->d_rtab;
   pr.dbg = tm_debug_words(nullptr);
+  pr.skip = getenv("ESCORT_TM_SKIP") ? atoi(getenv("ESCORT_TM_SKIP")) : 0;  // measurement only, see tmem_kernel.cuh
   plan->tm = tp;
   return 0;
 }
@@ -307,7 +334,8 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
 bool tmem_batch_fits(const escort_plan *plan, int num) {
   const TmParams &p = plan->tm->prm;
   const double lim = 2147483647.0;
-  return (double)num * p.IMG + p.TILE + p.SW < lim && (double)num * p.M * p.Ho * p.Wo < lim && (double)num * p.C * p.H * p.W < lim;
+  const double in_lim = kTmVariants[plan->tm->vidx].kind == 1 ? lim / 4 : lim;  // the self-fill loader table holds byte offsets
+  return (double)num * p.IMG + p.TILE + p.SW < lim && (double)num * p.M * p.Ho * p.Wo < lim && (double)num * p.C * p.H * p.W < in_lim;
 }
 
 int tmem_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,

@@ -42,9 +42,42 @@ struct TmParams {
   const uint4 *prog;      // record regions (16-byte units)
   const int2 *rtab;       // [ngroups * ogroups * nchunks] {offset, length} of a region in 16-byte units
   int *dbg;               // host-mapped debug words (bounded barrier waits report here before trapping), may be null
+  int skip;               // measurement only (ESCORT_TM_SKIP, results are WRONG): 1 = no window fill, 2 = no taps, 4 = no input loads
 };
 
 #ifndef ESCORT_TMEM_HOST_ONLY
+// ---- optional event trace (make TMTRACE=1; tools/tm_trace.py): lane 0 of every warp of CTA 0 logs {clock, code} ------
+#ifdef ESCORT_TM_TRACE
+static constexpr int kTmTraceWarps = 24, kTmTraceEvents = 4096;
+__device__ unsigned long long g_tm_trace[kTmTraceWarps * kTmTraceEvents];
+__device__ int g_tm_trace_n[kTmTraceWarps];
+// per-warp event counters live in the spare bytes behind the TMEM base slot of the barrier area (shared memory)
+__device__ __forceinline__ void tm_ev(unsigned code) {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    int *cnt = reinterpret_cast<int *>(smem_raw + (2 * 8 + 8 * 16) * 8 + 16) + w;
+    const int n = *cnt;
+    if (n < kTmTraceEvents) {
+      g_tm_trace[w * kTmTraceEvents + n] = ((unsigned long long)clock64() << 8) | code;
+      *cnt = n + 1;
+    }
+  }
+}
+__device__ __forceinline__ void tm_ev_init() {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if (threadIdx.x < kTmTraceWarps) reinterpret_cast<int *>(smem_raw + (2 * 8 + 8 * 16) * 8 + 16)[threadIdx.x] = 0;
+}
+__device__ __forceinline__ void tm_ev_fini() {
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  if (blockIdx.x == 0 && threadIdx.x < kTmTraceWarps) g_tm_trace_n[threadIdx.x] = reinterpret_cast<int *>(smem_raw + (2 * 8 + 8 * 16) * 8 + 16)[threadIdx.x];
+}
+#define TM_EV(code) tm_ev(code)
+#else
+#define TM_EV(code) do { } while (0)
+#define tm_ev_init() do { } while (0)
+#define tm_ev_fini() do { } while (0)
+#endif
 // ---- small PTX helpers ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tm_mbar_init(unsigned addr, unsigned count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
@@ -62,15 +95,20 @@ __device__ __forceinline__ void tm_mbar_wait(unsigned addr, unsigned parity, int
                : "memory");
   if (ok) return;
   unsigned long long t0 = 0;
+  unsigned backoff = 32;
   for (;;) {
-    // 64 cheap polls (try_wait suspends the warp until the barrier is touched or the hint expires), then one look at the clock
+    // Polls with a growing plain sleep in between.  try_wait's own suspension ends at every barrier event of the CTA
+    // (hundreds of cp.async arrivals per chunk), so four waiting warps polled ~70 times per wait and took about a
+    // third of their scheduler's issue slots from the one warp everybody was waiting for (profiles/r02_ncu_*_polls.txt).
 #pragma unroll 1
     for (int i = 0; i < 64; ++i) {
+      asm volatile("nanosleep.u32 %0;" ::"r"(backoff));
       asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                    : "=r"(ok)
                    : "r"(addr), "r"(parity)
                    : "memory");
       if (ok) return;
+      if (backoff < 256) backoff += backoff >> 1;
     }
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -226,6 +264,7 @@ __device__ __forceinline__ void tm_issue_load(const TmParams &p, int num, const 
   const int ui = it / p.nchunks, c = it - ui * p.nchunks;
   const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
   const int s = it % p.NS;
+  TM_EV(7);
   if (ui != ls.tab_unit) {
     // per-unit loader table: entry (step j, lane) = {source element offset of the position inside channel 0's batch
     // (-1: zero fill), skewed destination byte offset inside a staged channel row (-1: outside the staged range)}.
@@ -256,11 +295,12 @@ __device__ __forceinline__ void tm_issue_load(const TmParams &p, int num, const 
     asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");
   }
   if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
+  TM_EV(8);
   const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
   const int nch = min(p.CI, p.Cg - c * p.CI);
   const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
   const unsigned row_bytes = (unsigned)p.SWP * 4u;
-  for (int j = lw; j < p.ltab_n; j += NL) {  // this warp's table steps, all channels of the chunk
+  for (int j = lw; j < ((p.skip & 4) ? 0 : p.ltab_n); j += NL) {  // this warp's table steps, all channels of the chunk
     const int2 e = ltab[j * 32 + lane];
     if (e.y >= 0) {
       const float *src = e.x >= 0 ? src0 + e.x : bottom;
@@ -282,6 +322,7 @@ __device__ __forceinline__ void tm_issue_load(const TmParams &p, int num, const 
     for (int i = lw * 32 + lane; i < r.y; i += NL * 32) tm_cp_async16(dst + 16u * i, src + i);
   }
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
+  TM_EV(9);
 }
 
 // ---- producer warps (NPW / 4 per TMEM lane quadrant): shared memory -> TMEM windows ------------------------------------
@@ -311,7 +352,9 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
   for (int it = 0; it < total; ++it) {
     if (!LC && it + LA < total) tm_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, it + LA, pw, lane);
     const int s = it % p.NS;
+    TM_EV(11);
     tm_mbar_wait(smem_full + 8 * s, (unsigned)((it / p.NS) & 1), 2, p.dbg);
+    TM_EV(12);
     const int c = it % p.nchunks;
     const int nch = min(p.CI, p.Cg - c * p.CI);
     const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
@@ -327,10 +370,11 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
         tm_mbar_wait(tm_empty + 8 * slot, (round - 1) & 1u, 3, p.dbg);
         tm_fence_after();
       }
+      TM_EV(13);
       const int chn = min(p.CHS, nch - ch0);
       unsigned row_addr = stage_addr + (unsigned)(ch0 * p.SWP) * 4u;
       uint32_t tcol = tq + slot * (unsigned)(p.CHS * p.SLOTW);
-      for (int k = 0; k < chn; ++k, row_addr += (unsigned)p.SWP * 4u, tcol += (unsigned)p.SLOTW) {
+      for (int k = 0; k < ((p.skip & 1) ? 0 : chn); ++k, row_addr += (unsigned)p.SWP * 4u, tcol += (unsigned)p.SLOTW) {
         // the channel window in 16-column blocks, FB per round: all the 128-bit loads first, then the TMEM stores
         int b0 = 0;
 #define TM_LDS128(B, J) asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4+" #J "*16];" : "=r"(v[B][4 * J]), "=r"(v[B][4 * J + 1]), "=r"(v[B][4 * J + 2]), "=r"(v[B][4 * J + 3]) : "r"(a))
@@ -355,6 +399,7 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
 #undef TM_LDS128
       }
       tm_wait_st();
+      TM_EV(14);
       tm_fence_before();
       __syncwarp();
       if (lane == 0) tm_mbar_arrive(tm_full + 8 * slot);
@@ -387,6 +432,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
   const unsigned tm_full0 = smem_base + 16 * kTmMaxStages, tm_empty0 = tm_full0 + 4 * 8 * kTmMaxSlots;
   uint32_t *tbase_slot = reinterpret_cast<uint32_t *>(smem_raw + (2 * kTmMaxStages + 8 * kTmMaxSlots) * 8);
 
+  tm_ev_init();
   if (tid == 0) {
     for (int s = 0; s < p.NS; ++s) {
       tm_mbar_init(smem_full + 8 * s, (LC ? NCW : NPW) * 32);  // every loader thread arrives through its cp.asyncs
@@ -439,7 +485,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
           tm_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, kload, wid, lane);
           ++kload;
         }
+        TM_EV(1);
         tm_mbar_wait(smem_full + 8 * st, ph, 4, p.dbg);
+        TM_EV(2);
         const unsigned region = smem_base + p.stage0_off + st * p.stage_bytes + p.in_bytes;
         unsigned rp;  // this warp's records (8 bytes each: {TMEM column inside the slot group, fp32 weight})
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rp) : "r"(region + 4u * (unsigned)wid));
@@ -455,8 +503,9 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
           cp += 8;
           tm_mbar_wait(tm_full + 8 * slot, sph, 5, p.dbg);
           tm_fence_after();
+          TM_EV(3);
           const uint32_t tslot = tq + slot * slot_cols;
-          if ((cnt_lo | cnt_hi) != 0u) {
+          if ((cnt_lo | cnt_hi) != 0u && !(p.skip & 2)) {
 #pragma unroll
             for (int o = 0; o < OT; ++o) {
               unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
@@ -480,6 +529,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
               }
             }
           }
+          TM_EV(4);
           tm_fence_before();
           __syncwarp();
           if (lane == 0) tm_mbar_arrive(tm_empty + 8 * slot);
@@ -496,6 +546,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
         }
       }
       // ---- epilogue: bias + ReLU, lane-major tile -> (swizzled) shared memory -> coalesced predicated stores ----
+      TM_EV(5);
       const TmUnit uc = tm_decode_unit(p, u);
       const int blk = uc.og * NCW + wid;
       if (blk < p.nblk) {
@@ -556,12 +607,15 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
           __syncwarp();
         }
       }
+      TM_EV(6);
     }
   }
   tm_fence_before();
   __syncthreads();
+  tm_ev_fini();
   if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
 }
+
 #endif  // !ESCORT_TMEM_HOST_ONLY
 
 }  // namespace escort

@@ -50,7 +50,8 @@ struct TmVariant {
   X(16, 4, 16)                 \
   X(16, 6, 12)                 \
   X(16, 4, 12)                 \
-  X(16, 3, 16)
+  X(16, 3, 16)                 \
+  X(16, 8, 8)
 #define ESCORT_TM2_ROW(T, OT, NCW) {T, OT, NCW, 0, 0, 0, 1, 1, "sconv_tmem2_t" #T "_o" #OT "_w" #NCW, (const void *)&sconv_tmem2_kernel<T, OT, NCW>},
 static const TmVariant kTmVariants[] = {ESCORT_TM_VARIANTS(ESCORT_TM_ROW) ESCORT_TM2_VARIANTS(ESCORT_TM2_ROW)};
 static constexpr int kNumTmVariants = (int)(sizeof(kTmVariants) / sizeof(kTmVariants[0]));
@@ -241,7 +242,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
       r.o = oc_slot[z.oc];
       r.ic = icl; r.kh = z.kh; r.kw = z.kw;
       r.col = (unsigned)((in_chunk % CHS) * SLOTW + z.kh * g.dilation_h * PW + z.kw * g.dilation_w);
-      if (V.kind == 1) r.col |= (unsigned)((w & 3) * 32) << 16;  // absolute TMEM address: the warp's lane quadrant, buffer 0
+      r.col |= (unsigned)((w & 3) * 32) << 16;  // absolute TMEM address: the warp's lane quadrant (slot / buffer added by the kernel)
       r.val = z.val;
       r.src = (int)j;
       buckets[(((size_t)gi * ogroups + og) * nchunks + c) * NCW + w].push_back(r);
@@ -273,7 +274,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
               words.push_back(__builtin_bit_cast(unsigned, r.val));
             }
           }
-          if (V.kind == 1) words.resize(words.size() + 8, 0u);  // the record walk prefetches up to 32 bytes past the last record
+          words.resize(words.size() + 8, 0u);  // the record walk prefetches up to 32 bytes past the last record
           while (words.size() % 4) words.push_back(0u);
           const int len16 = (int)((words.size() - region_start) / 4);
           rtab[((size_t)gi * ogroups + og) * nchunks + c] = make_int2((int)(region_start / 4), len16);
@@ -334,7 +335,7 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
 bool tmem_batch_fits(const escort_plan *plan, int num) {
   const TmParams &p = plan->tm->prm;
   const double lim = 2147483647.0;
-  const double in_lim = kTmVariants[plan->tm->vidx].kind == 1 ? lim / 4 : lim;  // the self-fill loader table holds byte offsets
+  const double in_lim = lim / 4;  // the loader table holds byte offsets
   return (double)num * p.IMG + p.TILE + p.SW < lim && (double)num * p.M * p.Ho * p.Wo < lim && (double)num * p.C * p.H * p.W < in_lim;
 }
 

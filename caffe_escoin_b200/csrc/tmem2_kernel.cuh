@@ -20,186 +20,6 @@
 namespace escort {
 #ifndef ESCORT_TMEM_HOST_ONLY
 
-static constexpr int kTm2BufCols = 256;  // TMEM columns per buffer
-
-// One output channel's records of one slot group: n records of {absolute TMEM address, weight} at shared address rp
-// (advanced past them).  Accumulation order = record order (the reference's CSR order).  Reads up to 32 bytes past the
-// last record (prefetch; the host pads every region).
-#define TM2_T16 "{t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}"
-#define TM2_U16 "{u0,u1,u2,u3,u4,u5,u6,u7,u8,u9,u10,u11,u12,u13,u14,u15}"
-#define TM2_PACK(P, R)                                                                                                    \
-  "mov.b64 " #P "0, {" #R "0, " #R "1};\n\tmov.b64 " #P "1, {" #R "2, " #R "3};\n\tmov.b64 " #P "2, {" #R "4, " #R "5};\n\t"         \
-  "mov.b64 " #P "3, {" #R "6, " #R "7};\n\tmov.b64 " #P "4, {" #R "8, " #R "9};\n\tmov.b64 " #P "5, {" #R "10, " #R "11};\n\t"      \
-  "mov.b64 " #P "6, {" #R "12, " #R "13};\n\tmov.b64 " #P "7, {" #R "14, " #R "15};\n\t"
-#define TM2_FMA8(W, P)                                                                                                    \
-  "fma.rn.f32x2 %0, " #W ", " #P "0, %0;\n\tfma.rn.f32x2 %1, " #W ", " #P "1, %1;\n\tfma.rn.f32x2 %2, " #W ", " #P "2, %2;\n\t"     \
-  "fma.rn.f32x2 %3, " #W ", " #P "3, %3;\n\tfma.rn.f32x2 %4, " #W ", " #P "4, %4;\n\tfma.rn.f32x2 %5, " #W ", " #P "5, %5;\n\t"     \
-  "fma.rn.f32x2 %6, " #W ", " #P "6, %6;\n\tfma.rn.f32x2 %7, " #W ", " #P "7, %7;\n\t"
-template <int BUF>
-__device__ __forceinline__ void tm2_section16(unsigned long long (&a)[8], unsigned &rp, unsigned n) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b32 n2, c0, w0, c1, w1;\n\t"
-      ".reg .b32 t<16>, u<16>;\n\t"
-      ".reg .b64 x<8>, y<8>, ww, vv;\n\t"
-      "and.b32 n2, %9, 1;\n\t"
-      "setp.eq.u32 p, n2, 0;\n\t"
-      "@p bra TM2_PAIRS;\n\t"
-      "ld.shared.v2.u32 {c0, w0}, [%8];\n\t"
-      "add.u32 %8, %8, 8;\n\t"
-      "add.u32 c0, c0, %10;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [c0];\n\t"
-      "mov.b64 ww, {w0, w0};\n\t"
-      "tcgen05.wait::ld.sync.aligned;\n\t"
-      TM2_PACK(x, t)
-      TM2_FMA8(ww, x)
-      "TM2_PAIRS:\n\t"
-      "shr.u32 n2, %9, 1;\n\t"
-      "setp.eq.u32 p, n2, 0;\n\t"
-      "@p bra TM2_DONE;\n\t"
-      "ld.shared.v2.u32 {c0, w0}, [%8];\n\t"
-      "ld.shared.v2.u32 {c1, w1}, [%8+8];\n\t"
-      "TM2_LOOP:\n\t"
-      "add.u32 c0, c0, %10;\n\t"
-      "add.u32 c1, c1, %10;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [c0];\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_U16 ", [c1];\n\t"
-      "mov.b64 ww, {w0, w0};\n\t"
-      "mov.b64 vv, {w1, w1};\n\t"
-      "ld.shared.v2.u32 {c0, w0}, [%8+16];\n\t"
-      "ld.shared.v2.u32 {c1, w1}, [%8+24];\n\t"
-      "add.u32 %8, %8, 16;\n\t"
-      "tcgen05.wait::ld.sync.aligned;\n\t"
-      TM2_PACK(x, t)
-      TM2_PACK(y, u)
-      TM2_FMA8(ww, x)
-      TM2_FMA8(vv, y)
-      "sub.u32 n2, n2, 1;\n\t"
-      "setp.ne.u32 p, n2, 0;\n\t"
-      "@p bra TM2_LOOP;\n\t"
-      "TM2_DONE:\n\t"
-      "}"
-      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7]), "+r"(rp)
-      : "r"(n), "n"(BUF * kTm2BufCols)
-      : "memory");
-}
-
-// ring position of a chunk: unit, chunk inside the unit, shared-memory stage and its phase parity
-struct Tm2Pos {
-  int u, c;
-  unsigned st, ph;
-};
-__device__ __forceinline__ void tm2_advance(const TmParams &p, Tm2Pos &x) {
-  if (++x.c == p.nchunks) {
-    x.c = 0;
-    x.u += (int)gridDim.x;
-  }
-  if (++x.st == (unsigned)p.NS) {
-    x.st = 0;
-    x.ph ^= 1u;
-  }
-}
-
-// ---- loader: the chunk at ring position `ld` global -> shared memory (4-byte cp.async driven by the per-unit table) --
-struct Tm2Load {
-  Tm2Pos pos;
-  int count;      // chunks issued so far
-  int tab_unit;   // unit the loader table was built for
-  int chan0;      // first input channel of the unit's conv group
-  const int2 *rt; // the unit's row of the region table
-  int2 r;         // region {offset, length} of `pos` (fetched one call ahead: a dependent global load otherwise)
-};
-template <int NCW>
-__device__ __forceinline__ void tm2_unit_setup(const TmParams &p, int num, unsigned char *smem_raw, Tm2Load &ls, int wid, int lane) {
-  const TmUnit uc = tm_decode_unit(p, ls.pos.u);
-  ls.tab_unit = ls.pos.u;
-  ls.chan0 = uc.cg * p.Cg;
-  ls.rt = p.rtab + ((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks;
-  int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
-  asm volatile("bar.sync 5, %0;" ::"n"(NCW * 32) : "memory");  // every warp is done with the previous unit's table
-  const int tile_start = uc.tile * p.TILE;
-  const int R0 = tile_start / p.PW;
-  const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
-  const int nxb = (p.PW + 31) >> 5;
-  const int lpr = 1 << p.lpr_shift;
-  for (int e = wid * 32 + lane; e < p.ltab_n * 32; e += NCW * 32) {
-    const int j = e >> 5, l = e & 31;
-    const int jr = j / nxb, xb = j - jr * nxb;
-    const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
-    int2 ent = make_int2(-1, -1);
-    if (row < nrows && x < p.PW) {
-      const int R = R0 + row;
-      const int d = R * p.PW + x - tile_start;
-      if (d >= 0 && d < p.SW) {
-        const int n = R / p.IMGR, yy = R - n * p.IMGR;
-        ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
-        if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = ((n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w)) * 4;  // byte offset
-      }
-    }
-    ltab[e] = ent;
-  }
-  asm volatile("bar.sync 5, %0;" ::"n"(NCW * 32) : "memory");
-}
-template <int NCW>
-__device__ __forceinline__ void tm2_issue_load(const TmParams &p, int num, const float *__restrict__ bottom, unsigned char *smem_raw,
-                                               unsigned smem_base, Tm2Load &ls, int wid, int lane) {
-  TM_EV(7);
-  if (ls.pos.u != ls.tab_unit) {
-    tm2_unit_setup<NCW>(p, num, smem_raw, ls, wid, lane);
-    ls.r = ls.rt[ls.pos.c];
-  }
-  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
-  if (ls.count >= p.NS) tm_mbar_wait(smem_empty + 8 * ls.pos.st, ls.pos.ph ^ 1u, 1, p.dbg);
-  TM_EV(8);
-  const int2 *ltab = reinterpret_cast<const int2 *>(smem_raw + p.ltab_off);
-  const unsigned stage_addr = smem_base + p.stage0_off + ls.pos.st * (unsigned)p.stage_bytes;
-  const int nch = min(p.CI, p.Cg - ls.pos.c * p.CI);
-  const size_t HW4 = (size_t)(p.H * p.W) * 4;
-  const char *src0 = reinterpret_cast<const char *>(bottom) + (size_t)(ls.chan0 + ls.pos.c * p.CI) * HW4;
-  const unsigned row_bytes = (unsigned)p.SWP * 4u;
-#define TM2_CP4(K) asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (K) * row_bytes), "l"(src + (K) * sstep), "r"(nbytes))
-#pragma unroll 1
-  for (int j = wid; j < ((p.skip & 4) ? 0 : p.ltab_n); j += NCW) {  // this warp's table steps, all channels of the chunk
-    const int2 e = ltab[j * 32 + lane];
-    if (e.y >= 0) {
-      const char *src = e.x >= 0 ? src0 + (unsigned)e.x : reinterpret_cast<const char *>(bottom);
-      const unsigned nbytes = e.x >= 0 ? 4u : 0u;
-      const size_t sstep = e.x >= 0 ? HW4 : 0;
-      unsigned dst = stage_addr + (unsigned)e.y;
-      int ch = nch;
-#pragma unroll 1
-      for (; ch >= 4; ch -= 4) {  // four copies back to back (ptxas pads a lone LDGSTS with dummy LDS)
-        TM2_CP4(0);
-        TM2_CP4(1);
-        TM2_CP4(2);
-        TM2_CP4(3);
-        src += 4 * sstep;
-        dst += 4 * row_bytes;
-      }
-      if (ch & 2) {
-        TM2_CP4(0);
-        TM2_CP4(1);
-        src += 2 * sstep;
-        dst += 2 * row_bytes;
-      }
-      if (ch & 1) TM2_CP4(0);
-    }
-  }
-#undef TM2_CP4
-  {  // record region of this (pass, chunk): contiguous 16-byte async copies
-    const uint4 *src = p.prog + ls.r.x;
-    const unsigned dst = stage_addr + p.in_bytes;
-#pragma unroll 1
-    for (int i = wid * 32 + lane; i < ls.r.y; i += NCW * 32) tm_cp_async16(dst + 16u * i, src + i);
-  }
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * ls.pos.st) : "memory");
-  ++ls.count;
-  tm2_advance(p, ls.pos);
-  if (ls.pos.u == ls.tab_unit) ls.r = ls.rt[ls.pos.c];  // next call's region (same unit: same table row)
-  TM_EV(9);
-}
-
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 template <int T, int OT, int NCW>
 __global__ void __launch_bounds__(NCW * 32, 1)
@@ -243,7 +63,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
   ls.count = 0;
   ls.tab_unit = -1;
   const int LA = p.NS - 2;  // chunks the loads run ahead
-  for (int k = 0; k < LA && k < total; ++k) tm2_issue_load<NCW>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
+  for (int k = 0; k < LA && k < total; ++k) tm2_issue_load<NCW, 5>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
 
   // this warp's share of one slot group's fill: 16-column blocks wa, wa + NQ, ... of the chn channel windows of the
   // staged rows at `rows`, two blocks (eight 128-bit loads) in flight, into the buffer at column tcol0
@@ -297,13 +117,21 @@ __global__ void __launch_bounds__(NCW * 32, 1)
 #pragma unroll
         for (int k = 0; k < T / 2; ++k) acc[o][k] = 0ull;
     }
-    if (ls.count < total) tm2_issue_load<NCW>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
+    if (ls.count < total) tm2_issue_load<NCW, 5>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
     // (this chunk's smem_full was waited for before its first slot group was filled)
     const unsigned stage_addr = smem_base + p.stage0_off + cur.st * (unsigned)p.stage_bytes;
     const unsigned region = stage_addr + p.in_bytes;
     unsigned rp;  // this warp's records (8 bytes each: {absolute TMEM address of the window in buffer 0, fp32 weight})
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rp) : "r"(region + 4u * (unsigned)wid));
     rp += region;
+    // With registers to spare (fewer than 16 warps) the next two records are carried across sections (tm2_section16's
+    // invariant: +5-9 %); at 128 registers the four extra live values make ptxas spill accumulators (-5 %).
+    constexpr bool CARRY = NCW < 16;
+    unsigned c0 = 0, w0 = 0, c1 = 0, w1 = 0;
+    if (CARRY) {
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(c0), "=r"(w0) : "r"(rp));
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+8];" : "=r"(c1), "=r"(w1) : "r"(rp));
+    }
     unsigned cp = region + p.hdr_counts_off + (unsigned)(wid * p.nsg) * 8u;  // per slot group: 8 tap counts (one byte per o)
     const int nch = min(p.CI, p.Cg - cur.c * p.CI);
     Tm2Pos nxt = cur;
@@ -337,10 +165,18 @@ __global__ void __launch_bounds__(NCW * 32, 1)
       if ((cnt_lo | cnt_hi) != 0u && !(p.skip & 2)) {
         if (buf == 0u) {
 #pragma unroll
-          for (int o = 0; o < OT; ++o) tm2_section16<0>(acc[o], rp, ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu);
+          for (int o = 0; o < OT; ++o) {
+            const unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
+            if constexpr (CARRY) tm2_section16<0>(acc[o], rp, n, c0, w0, c1, w1);
+            else tm2_section16_r(acc[o], rp, n, 0u);
+          }
         } else {
 #pragma unroll
-          for (int o = 0; o < OT; ++o) tm2_section16<1>(acc[o], rp, ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu);
+          for (int o = 0; o < OT; ++o) {
+            const unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
+            if constexpr (CARRY) tm2_section16<1>(acc[o], rp, n, c0, w0, c1, w1);
+            else tm2_section16_r(acc[o], rp, n, (unsigned)kTm2BufCols);
+          }
         }
       }
       TM_EV(4);

@@ -250,80 +250,240 @@ __device__ __forceinline__ TmUnit tm_decode_unit(const TmParams &p, int u) {
   return c;
 }
 
-// ---- loader (run by the NL compute warps, each a share of the table steps): one chunk global -> shared memory --------
-// 4-byte cp.async driven by a per-unit table; halo positions and images past the batch are zero-filled (src size 0).
-struct TmLoadState {
-  int tab_unit;  // unit the table in shared memory was built for
+static constexpr int kTm2BufCols = 256;  // TMEM columns per buffer
+
+// One output channel's records of one slot group: n records of {absolute TMEM address, weight} at shared address rp
+// (advanced past them).  Accumulation order = record order (the reference's CSR order).  Reads up to 32 bytes past the
+// last record (prefetch; the host pads every region).
+#define TM2_T16 "{t0,t1,t2,t3,t4,t5,t6,t7,t8,t9,t10,t11,t12,t13,t14,t15}"
+#define TM2_U16 "{u0,u1,u2,u3,u4,u5,u6,u7,u8,u9,u10,u11,u12,u13,u14,u15}"
+#define TM2_PACK(P, R)                                                                                                    \
+  "mov.b64 " #P "0, {" #R "0, " #R "1};\n\tmov.b64 " #P "1, {" #R "2, " #R "3};\n\tmov.b64 " #P "2, {" #R "4, " #R "5};\n\t"         \
+  "mov.b64 " #P "3, {" #R "6, " #R "7};\n\tmov.b64 " #P "4, {" #R "8, " #R "9};\n\tmov.b64 " #P "5, {" #R "10, " #R "11};\n\t"      \
+  "mov.b64 " #P "6, {" #R "12, " #R "13};\n\tmov.b64 " #P "7, {" #R "14, " #R "15};\n\t"
+#define TM2_FMA8(W, P)                                                                                                    \
+  "fma.rn.f32x2 %0, " #W ", " #P "0, %0;\n\tfma.rn.f32x2 %1, " #W ", " #P "1, %1;\n\tfma.rn.f32x2 %2, " #W ", " #P "2, %2;\n\t"     \
+  "fma.rn.f32x2 %3, " #W ", " #P "3, %3;\n\tfma.rn.f32x2 %4, " #W ", " #P "4, %4;\n\tfma.rn.f32x2 %5, " #W ", " #P "5, %5;\n\t"     \
+  "fma.rn.f32x2 %6, " #W ", " #P "6, %6;\n\tfma.rn.f32x2 %7, " #W ", " #P "7, %7;\n\t"
+// Invariant at entry and exit: (c0, w0) = the record at rp, (c1, w1) = the record at rp + 8 -- the next section's first
+// records are already in registers when it starts (their load overlapped this section's last FMAs).
+template <int BUF>
+__device__ __forceinline__ void tm2_section16(unsigned long long (&a)[8], unsigned &rp, unsigned n, unsigned &c0, unsigned &w0, unsigned &c1,
+                                              unsigned &w1) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 n2, ca, cb;\n\t"
+      ".reg .b32 t<16>, u<16>;\n\t"
+      ".reg .b64 x<8>, y<8>, ww, vv;\n\t"
+      "and.b32 n2, %13, 1;\n\t"
+      "setp.eq.u32 p, n2, 0;\n\t"
+      "@p bra TM2_PAIRS;\n\t"
+      "add.u32 ca, %9, %14;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [ca];\n\t"
+      "mov.b64 ww, {%10, %10};\n\t"
+      "mov.b32 %9, %11;\n\t"
+      "mov.b32 %10, %12;\n\t"
+      "ld.shared.v2.u32 {%11, %12}, [%8+16];\n\t"
+      "add.u32 %8, %8, 8;\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      TM2_PACK(x, t)
+      TM2_FMA8(ww, x)
+      "TM2_PAIRS:\n\t"
+      "shr.u32 n2, %13, 1;\n\t"
+      "setp.eq.u32 p, n2, 0;\n\t"
+      "@p bra TM2_DONE;\n\t"
+      "TM2_LOOP:\n\t"
+      "add.u32 ca, %9, %14;\n\t"
+      "add.u32 cb, %11, %14;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [ca];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_U16 ", [cb];\n\t"
+      "mov.b64 ww, {%10, %10};\n\t"
+      "mov.b64 vv, {%12, %12};\n\t"
+      "ld.shared.v2.u32 {%9, %10}, [%8+16];\n\t"
+      "ld.shared.v2.u32 {%11, %12}, [%8+24];\n\t"
+      "add.u32 %8, %8, 16;\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      TM2_PACK(x, t)
+      TM2_PACK(y, u)
+      TM2_FMA8(ww, x)
+      TM2_FMA8(vv, y)
+      "sub.u32 n2, n2, 1;\n\t"
+      "setp.ne.u32 p, n2, 0;\n\t"
+      "@p bra TM2_LOOP;\n\t"
+      "TM2_DONE:\n\t"
+      "}"
+      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7]), "+r"(rp), "+r"(c0), "+r"(w0),
+        "+r"(c1), "+r"(w1)
+      : "r"(n), "n"(BUF * kTm2BufCols)
+      : "memory");
+}
+
+// the same with the window base (slot group position in the TMEM ring) in a register
+__device__ __forceinline__ void tm2_section16_r(unsigned long long (&a)[8], unsigned &rp, unsigned n, unsigned base) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b32 n2, c0, w0, c1, w1;\n\t"
+      ".reg .b32 t<16>, u<16>;\n\t"
+      ".reg .b64 x<8>, y<8>, ww, vv;\n\t"
+      "and.b32 n2, %9, 1;\n\t"
+      "setp.eq.u32 p, n2, 0;\n\t"
+      "@p bra TM2_PAIRS;\n\t"
+      "ld.shared.v2.u32 {c0, w0}, [%8];\n\t"
+      "add.u32 %8, %8, 8;\n\t"
+      "add.u32 c0, c0, %10;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [c0];\n\t"
+      "mov.b64 ww, {w0, w0};\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      TM2_PACK(x, t)
+      TM2_FMA8(ww, x)
+      "TM2_PAIRS:\n\t"
+      "shr.u32 n2, %9, 1;\n\t"
+      "setp.eq.u32 p, n2, 0;\n\t"
+      "@p bra TM2_DONE;\n\t"
+      "ld.shared.v2.u32 {c0, w0}, [%8];\n\t"
+      "ld.shared.v2.u32 {c1, w1}, [%8+8];\n\t"
+      "TM2_LOOP:\n\t"
+      "add.u32 c0, c0, %10;\n\t"
+      "add.u32 c1, c1, %10;\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_T16 ", [c0];\n\t"
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 " TM2_U16 ", [c1];\n\t"
+      "mov.b64 ww, {w0, w0};\n\t"
+      "mov.b64 vv, {w1, w1};\n\t"
+      "ld.shared.v2.u32 {c0, w0}, [%8+16];\n\t"
+      "ld.shared.v2.u32 {c1, w1}, [%8+24];\n\t"
+      "add.u32 %8, %8, 16;\n\t"
+      "tcgen05.wait::ld.sync.aligned;\n\t"
+      TM2_PACK(x, t)
+      TM2_PACK(y, u)
+      TM2_FMA8(ww, x)
+      TM2_FMA8(vv, y)
+      "sub.u32 n2, n2, 1;\n\t"
+      "setp.ne.u32 p, n2, 0;\n\t"
+      "@p bra TM2_LOOP;\n\t"
+      "TM2_DONE:\n\t"
+      "}"
+      : "+l"(a[0]), "+l"(a[1]), "+l"(a[2]), "+l"(a[3]), "+l"(a[4]), "+l"(a[5]), "+l"(a[6]), "+l"(a[7]), "+r"(rp)
+      : "r"(n), "r"(base)
+      : "memory");
+}
+
+// ring position of a chunk: unit, chunk inside the unit, shared-memory stage and its phase parity
+struct Tm2Pos {
+  int u, c;
+  unsigned st, ph;
+};
+__device__ __forceinline__ void tm2_advance(const TmParams &p, Tm2Pos &x) {
+  if (++x.c == p.nchunks) {
+    x.c = 0;
+    x.u += (int)gridDim.x;
+  }
+  if (++x.st == (unsigned)p.NS) {
+    x.st = 0;
+    x.ph ^= 1u;
+  }
+}
+
+// ---- loader: the chunk at ring position `ld` global -> shared memory (4-byte cp.async driven by the per-unit table) --
+struct Tm2Load {
+  Tm2Pos pos;
+  int count;      // chunks issued so far
+  int tab_unit;   // unit the loader table was built for
+  int chan0;      // first input channel of the unit's conv group
+  const int2 *rt; // the unit's row of the region table
+  int2 r;         // region {offset, length} of `pos` (fetched one call ahead: a dependent global load otherwise)
 };
 template <int NL, int BAR>
-__device__ __forceinline__ void tm_issue_load(const TmParams &p, int num, const float *__restrict__ bottom, unsigned char *smem_raw,
-                                              unsigned smem_base, TmLoadState &ls, int it, int lw, int lane) {
-  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
+__device__ __forceinline__ void tm2_unit_setup(const TmParams &p, int num, unsigned char *smem_raw, Tm2Load &ls, int lw, int lane) {
+  const TmUnit uc = tm_decode_unit(p, ls.pos.u);
+  ls.tab_unit = ls.pos.u;
+  ls.chan0 = uc.cg * p.Cg;
+  ls.rt = p.rtab + ((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks;
   int2 *ltab = reinterpret_cast<int2 *>(smem_raw + p.ltab_off);
-  const int HW = p.H * p.W;
-  const int ui = it / p.nchunks, c = it - ui * p.nchunks;
-  const TmUnit uc = tm_decode_unit(p, (int)blockIdx.x + ui * (int)gridDim.x);
-  const int s = it % p.NS;
-  TM_EV(7);
-  if (ui != ls.tab_unit) {
-    // per-unit loader table: entry (step j, lane) = {source element offset of the position inside channel 0's batch
-    // (-1: zero fill), skewed destination byte offset inside a staged channel row (-1: outside the staged range)}.
-    // A step = RO padded rows x LPR columns (or one 32-column block of a wide row).
-    ls.tab_unit = ui;
-    asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");  // every loader warp is done with the previous unit's table
-    const int tile_start = uc.tile * p.TILE;
-    const int R0 = tile_start / p.PW;
-    const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
-    const int nxb = (p.PW + 31) >> 5;
-    const int lpr = 1 << p.lpr_shift;
-    for (int e = lw * 32 + lane; e < p.ltab_n * 32; e += NL * 32) {
-      const int j = e >> 5, l = e & 31;
-      const int jr = j / nxb, xb = j - jr * nxb;
-      const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
-      int2 ent = make_int2(-1, -1);
-      if (row < nrows && x < p.PW) {
-        const int R = R0 + row;
-        const int d = R * p.PW + x - tile_start;
-        if (d >= 0 && d < p.SW) {
-          const int n = R / p.IMGR, yy = R - n * p.IMGR;
-          ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
-          if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = (n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w);
-        }
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");  // every loader warp is done with the previous unit's table
+  const int tile_start = uc.tile * p.TILE;
+  const int R0 = tile_start / p.PW;
+  const int nrows = (tile_start + p.SW - 1) / p.PW - R0 + 1;
+  const int nxb = (p.PW + 31) >> 5;
+  const int lpr = 1 << p.lpr_shift;
+  for (int e = lw * 32 + lane; e < p.ltab_n * 32; e += NL * 32) {
+    const int j = e >> 5, l = e & 31;
+    const int jr = j / nxb, xb = j - jr * nxb;
+    const int row = jr * p.RO + (l >> p.lpr_shift), x = (l & (lpr - 1)) + 32 * xb;
+    int2 ent = make_int2(-1, -1);
+    if (row < nrows && x < p.PW) {
+      const int R = R0 + row;
+      const int d = R * p.PW + x - tile_start;
+      if (d >= 0 && d < p.SW) {
+        const int n = R / p.IMGR, yy = R - n * p.IMGR;
+        ent.y = (int)((tm_skew((unsigned)d >> 2) << 4) + (((unsigned)d & 3u) << 2));
+        if (n < num && yy >= p.pad_h && x >= p.pad_w) ent.x = ((n * p.C * p.H + (yy - p.pad_h)) * p.W + (x - p.pad_w)) * 4;  // byte offset
       }
-      ltab[e] = ent;
     }
-    asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");
+    ltab[e] = ent;
   }
-  if (it >= p.NS) tm_mbar_wait(smem_empty + 8 * s, (unsigned)((it / p.NS - 1) & 1), 1, p.dbg);
+  asm volatile("bar.sync %0, %1;" ::"n"(BAR), "n"(NL * 32) : "memory");
+}
+template <int NL, int BAR>
+__device__ __forceinline__ void tm2_issue_load(const TmParams &p, int num, const float *__restrict__ bottom, unsigned char *smem_raw,
+                                               unsigned smem_base, Tm2Load &ls, int lw, int lane) {
+  TM_EV(7);
+  if (ls.pos.u != ls.tab_unit) {
+    tm2_unit_setup<NL, BAR>(p, num, smem_raw, ls, lw, lane);
+    ls.r = ls.rt[ls.pos.c];
+  }
+  const unsigned smem_full = smem_base, smem_empty = smem_base + 8 * kTmMaxStages;
+  if (ls.count >= p.NS) tm_mbar_wait(smem_empty + 8 * ls.pos.st, ls.pos.ph ^ 1u, 1, p.dbg);
   TM_EV(8);
-  const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
-  const int nch = min(p.CI, p.Cg - c * p.CI);
-  const float *src0 = bottom + (size_t)(uc.cg * p.Cg + c * p.CI) * HW;
+  const int2 *ltab = reinterpret_cast<const int2 *>(smem_raw + p.ltab_off);
+  const unsigned stage_addr = smem_base + p.stage0_off + ls.pos.st * (unsigned)p.stage_bytes;
+  const int nch = min(p.CI, p.Cg - ls.pos.c * p.CI);
+  const size_t HW4 = (size_t)(p.H * p.W) * 4;
+  const char *src0 = reinterpret_cast<const char *>(bottom) + (size_t)(ls.chan0 + ls.pos.c * p.CI) * HW4;
   const unsigned row_bytes = (unsigned)p.SWP * 4u;
+#define TM2_CP4(K) asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + (K) * row_bytes), "l"(src + (K) * sstep), "r"(nbytes))
+#pragma unroll 1
   for (int j = lw; j < ((p.skip & 4) ? 0 : p.ltab_n); j += NL) {  // this warp's table steps, all channels of the chunk
     const int2 e = ltab[j * 32 + lane];
     if (e.y >= 0) {
-      const float *src = e.x >= 0 ? src0 + e.x : bottom;
+      const char *src = e.x >= 0 ? src0 + (unsigned)e.x : reinterpret_cast<const char *>(bottom);
       const unsigned nbytes = e.x >= 0 ? 4u : 0u;
-      const size_t sstep = e.x >= 0 ? (size_t)HW : 0;
+      const size_t sstep = e.x >= 0 ? HW4 : 0;
       unsigned dst = stage_addr + (unsigned)e.y;
-#pragma unroll 2
-      for (int ch = 0; ch < nch; ++ch) {
-        tm_cp_async4(dst, src, nbytes);
-        src += sstep;
-        dst += row_bytes;
+      int ch = nch;
+#pragma unroll 1
+      for (; ch >= 4; ch -= 4) {  // four copies back to back (ptxas pads a lone LDGSTS with dummy LDS)
+        TM2_CP4(0);
+        TM2_CP4(1);
+        TM2_CP4(2);
+        TM2_CP4(3);
+        src += 4 * sstep;
+        dst += 4 * row_bytes;
       }
+      if (ch & 2) {
+        TM2_CP4(0);
+        TM2_CP4(1);
+        src += 2 * sstep;
+        dst += 2 * row_bytes;
+      }
+      if (ch & 1) TM2_CP4(0);
     }
   }
+#undef TM2_CP4
   {  // record region of this (pass, chunk): contiguous 16-byte async copies
-    const int2 r = p.rtab[((size_t)uc.cg * p.ogroups + uc.og) * p.nchunks + c];
-    const uint4 *src = p.prog + r.x;
+    const uint4 *src = p.prog + ls.r.x;
     const unsigned dst = stage_addr + p.in_bytes;
-    for (int i = lw * 32 + lane; i < r.y; i += NL * 32) tm_cp_async16(dst + 16u * i, src + i);
+#pragma unroll 1
+    for (int i = lw * 32 + lane; i < ls.r.y; i += NL * 32) tm_cp_async16(dst + 16u * i, src + i);
   }
-  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * s) : "memory");
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_full + 8 * ls.pos.st) : "memory");
+  ++ls.count;
+  tm2_advance(p, ls.pos);
+  if (ls.pos.u == ls.tab_unit) ls.r = ls.rt[ls.pos.c];  // next call's region (same unit: same table row)
   TM_EV(9);
 }
+
 
 // ---- producer warps (NPW / 4 per TMEM lane quadrant): shared memory -> TMEM windows ------------------------------------
 // NPW producer warps = NPW / 4 per quadrant; pw = producer warp index, quadrant = pw % 4, pa = pw / 4 = which share of a
@@ -345,17 +505,22 @@ __device__ __forceinline__ void tm_producer_loop(const TmParams &p, int num, con
 
   // lane's first chunk of a window (before the skew): lane * T/4; a 16-column block never straddles a pad chunk
   const unsigned lane_chunk = (unsigned)lane * (T / 4);
-  TmLoadState ls = {-1};
+  Tm2Load ls;
+  ls.pos = {(int)blockIdx.x, 0, 0u, 0u};
+  ls.count = 0;
+  ls.tab_unit = -1;
   const int LA = p.NS - 2;  // chunks the loads run ahead: the stage being refilled was released a whole chunk ago
   if (!LC)
-    for (int it = 0; it < LA && it < total; ++it) tm_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, it, pw, lane);
+    for (int it = 0; it < LA && it < total; ++it) tm2_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, pw, lane);
+  Tm2Pos cur = {(int)blockIdx.x, 0, 0u, 0u};  // ring position of chunk `it` (no divisions in the loop)
   for (int it = 0; it < total; ++it) {
-    if (!LC && it + LA < total) tm_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, it + LA, pw, lane);
-    const int s = it % p.NS;
+    if (!LC && ls.count < total) tm2_issue_load<NPW, 2>(p, num, bottom, smem_raw, smem_base, ls, pw, lane);
+    const int s = (int)cur.st;
     TM_EV(11);
-    tm_mbar_wait(smem_full + 8 * s, (unsigned)((it / p.NS) & 1), 2, p.dbg);
+    tm_mbar_wait(smem_full + 8 * s, cur.ph, 2, p.dbg);
     TM_EV(12);
-    const int c = it % p.nchunks;
+    const int c = cur.c;
+    tm2_advance(p, cur);
     const int nch = min(p.CI, p.Cg - c * p.CI);
     const unsigned stage_addr = smem_base + p.stage0_off + (unsigned)s * p.stage_bytes;
     for (int ch0 = 0; ch0 < nch; ch0 += p.CHS) {
@@ -453,6 +618,10 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
   __syncthreads();
   tm_fence_after();
   const uint32_t tbase = *tbase_slot;
+  if (tbase != 0u) {  // the records hold absolute addresses: the CTA owns all 512 columns, so its base is column 0
+    if (p.dbg && tid == 0 && atomicCAS(p.dbg, 0, 9) == 0) p.dbg[1] = (int)tbase;
+    __trap();
+  }
 
   if (wid >= NCW) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(PREGS) : "memory");
@@ -461,7 +630,6 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(CREGS) : "memory");
     const int q = wid & 3;
     const unsigned tm_full = tm_full0 + (unsigned)q * 8 * kTmMaxSlots, tm_empty = tm_empty0 + (unsigned)q * 8 * kTmMaxSlots;
-    const uint32_t tq = tbase + ((uint32_t)(q * 32) << 16);
     const unsigned slot_cols = (unsigned)(p.CHS * p.SLOTW);
     unsigned long long acc[OT][T / 2];
     unsigned st = 0, ph = 0;          // shared-memory stage ring
@@ -470,9 +638,11 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
     const int my_units = blockIdx.x < (unsigned)nunits ? (nunits - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int total = my_units * p.nchunks;
     const int LA = p.NS - 2;  // chunks the loads run ahead: the stage being refilled was released a whole chunk ago
-    TmLoadState ls = {-1};
-    int kload = 0;
-    for (; LC && kload < LA && kload < total; ++kload) tm_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, kload, wid, lane);
+    Tm2Load ls;
+    ls.pos = {(int)blockIdx.x, 0, 0u, 0u};
+    ls.count = 0;
+    ls.tab_unit = -1;
+    for (int k = 0; LC && k < LA && k < total; ++k) tm2_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
 #pragma unroll 1
     for (int u = blockIdx.x; u < nunits; u += gridDim.x) {
 #pragma unroll
@@ -481,10 +651,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
         for (int k = 0; k < T / 2; ++k) acc[o][k] = 0ull;
 #pragma unroll 1
       for (int c = 0; c < p.nchunks; ++c) {
-        if (LC && kload < total) {
-          tm_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, kload, wid, lane);
-          ++kload;
-        }
+        if (LC && ls.count < total) tm2_issue_load<NCW, 1>(p, num, bottom, smem_raw, smem_base, ls, wid, lane);
         TM_EV(1);
         tm_mbar_wait(smem_full + 8 * st, ph, 4, p.dbg);
         TM_EV(2);
@@ -492,7 +659,7 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
         unsigned rp;  // this warp's records (8 bytes each: {TMEM column inside the slot group, fp32 weight})
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rp) : "r"(region + 4u * (unsigned)wid));
         rp += region;
-        unsigned col, wbits;  // the NEXT record, always one tap ahead (its load overlaps the current tap's FMAs)
+        unsigned col = 0, wbits = 0;  // the NEXT record, always one tap ahead (its load overlaps the current tap's FMAs)
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(col), "=r"(wbits) : "r"(rp));
         unsigned cp = region + p.hdr_counts_off + (unsigned)(wid * p.nsg) * 8u;  // per slot group: 8 tap counts (one byte per o)
         const int nch = min(p.CI, p.Cg - c * p.CI);
@@ -504,11 +671,17 @@ __global__ void __launch_bounds__((NCW + NPW) * 32, 1)
           tm_mbar_wait(tm_full + 8 * slot, sph, 5, p.dbg);
           tm_fence_after();
           TM_EV(3);
-          const uint32_t tslot = tq + slot * slot_cols;
+          const uint32_t tslot = slot * slot_cols;  // (the records carry the quadrant's lane bits: absolute addresses)
           if ((cnt_lo | cnt_hi) != 0u && !(p.skip & 2)) {
 #pragma unroll
             for (int o = 0; o < OT; ++o) {
               unsigned n = ((o < 4 ? cnt_lo : cnt_hi) >> (8 * (o & 3))) & 0xffu;
+#ifdef ESCORT_TM_SECTION_WALK  // measured: the C++ walk below (next record prefetched across sections) is 3-4 % faster here
+              if constexpr (T == 16) {
+                tm2_section16_r(acc[o], rp, n, tslot);
+                continue;
+              }
+#endif
               // (col, wbits) always hold the NEXT record; an odd tap first, then pairs (half the loop overhead per tap)
               if (n & 1u) {
                 const uint32_t taddr = tslot + col;

@@ -109,7 +109,7 @@ int tile_regather(escort_plan *plan, const int4 *meta, cudaStream_t stream);
 int tmem_num_variants();
 bool tmem_variant_applies(const escort_plan *plan, int tv);
 int tmem_choose_variant(const escort_plan *plan);
-int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream);
+int tmem_plan_build(escort_plan *plan, int tv, int layout_rank, cudaStream_t stream);
 void tmem_plan_free(TmemPlan *tp);
 bool tmem_batch_fits(const escort_plan *plan, int num);
 int tmem_forward(escort_plan *plan, int num, const float *bottom, const float *bias, int fuse_relu, float *top,

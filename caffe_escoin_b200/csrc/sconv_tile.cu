@@ -235,11 +235,11 @@ int tile_plan_build(escort_plan *plan, int variant, cudaStream_t stream) {
   plan->tm = nullptr;
   const escort_geom &g = plan->g;
   // the TMEM-window kernel (sconv_tmem.cu): explicit variant ids above the tile variants, and the default wherever it applies
-  if (variant > kNumVariants) return layout_rank == 0 ? tmem_plan_build(plan, variant - kNumVariants - 1, stream) : 0;
+  if (variant > kNumVariants) return tmem_plan_build(plan, variant - kNumVariants - 1, layout_rank, stream);
   if (variant <= 0 && !g_building_w) {
     const int tv = tmem_choose_variant(plan);
     if (tv >= 0) {
-      const int rc = tmem_plan_build(plan, tv, stream);
+      const int rc = tmem_plan_build(plan, tv, layout_rank, stream);
       if (rc || plan->tm) return rc;
     }
   }

@@ -156,8 +156,9 @@ int tmem_choose_variant(const escort_plan *plan) {
   return -1;
 }
 
-int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
+int tmem_plan_build(escort_plan *plan, int tv, int layout_rank, cudaStream_t stream) {
   plan->tm = nullptr;
+  if (layout_rank > 3) return 0;
   if (!tmem_variant_applies(plan, tv)) return 0;
   const TmVariant &V = kTmVariants[tv];
   const escort_geom &g = plan->g;
@@ -167,11 +168,21 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
   const int PW = g.width + g.pad_w, IMGR = g.height + g.pad_h, IMG = IMGR * PW;
   const int HALO = (KH - 1) * g.dilation_h * PW + (KW - 1) * g.dilation_w;
   const int SLOTW = round_up(T + HALO, 16);
-  int CHS = std::max(1, std::min(4, 512 / (3 * SLOTW)));  // three slot groups in flight; larger groups = fewer hand-shakes per tap
-  if (V.kind == 1) CHS = std::max(1, std::min(8, 256 / SLOTW));  // two buffers of 256 columns; one barrier per slot group
+  // Channels per slot group.  Measured (profiles/r02_tm_knob_sweep.txt): the per-group cost (hand-shake, tap-count
+  // decode, ring bookkeeping) dominates the slack a deeper TMEM ring buys -- two slot groups of as many windows as fit
+  // beat three or five smaller ones by 5-12 % on every 3x3 layer, and three large shared-memory stages beat four or
+  // five smaller ones by 2-4 %.  layout_rank 1..3 are the runner-up layouts the autotuner re-times.
+  const int chs_max = std::max(1, std::min(8, 256 / SLOTW));
+  int CHS = chs_max;
+  int ns_min = 3;
+  if (layout_rank == 1) ns_min = 4;
+  if (layout_rank == 2) CHS = std::max(1, chs_max - 1);
+  if (layout_rank == 3) CHS = std::max(1, std::min(chs_max, 512 / (3 * SLOTW)));  // three slot groups in flight
+  if (layout_rank >= 2 && CHS == chs_max) return 0;  // no such layout candidate
   if (const char *e = getenv("ESCORT_TM_CHS")) CHS = std::max(1, std::min(atoi(e), 512 / (2 * SLOTW)));  // tuning knob
   while (CHS > 1 && CHS * KH * KW > 255) --CHS;
   const int NSLOT = V.kind == 1 ? 2 : std::min(512 / (CHS * SLOTW), kTmMaxSlots);
+  if (const char *e = getenv("ESCORT_TM_NSMIN")) ns_min = atoi(e);  // tuning knob
   if (NSLOT < 2) return 0;
   const int TILE = 32 * T;
   const int SW = round_up(TILE - T + SLOTW, 32);
@@ -282,8 +293,6 @@ int tmem_plan_build(escort_plan *plan, int tv, cudaStream_t stream) {
         }
     stage_bytes = in_bytes + round_up(max_region16 * 16, 128);
     NS = (int)std::min<long>(budget / stage_bytes, (long)kTmMaxStages);
-    // self-fill kernel: three larger stages (loads run one chunk ahead) beat four smaller ones by 2-3 % (fewer chunks)
-    const int ns_min = getenv("ESCORT_TM_NSMIN") ? atoi(getenv("ESCORT_TM_NSMIN")) : (V.kind == 1 ? 3 : 4);  // tuning knob
     if (NS >= ns_min || (NS >= 3 && CI == CHS)) break;
     if (CI == CHS) return 0;  // does not fit
     CI = std::max(CHS, (CI * 3 / 4) / CHS * CHS);

@@ -28,6 +28,8 @@ EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sco
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
            "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
+           "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
+           "escort_caffemodel_find", "escort_caffemodel_layer", "escort_caffemodel_blob", "escort_prune_magnitude",
            "escort_last_error", "escort_version"]
 
 lib.escort_last_error.restype = C.c_char_p
@@ -44,6 +46,14 @@ lib.escort_plan_autotune.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_autotune_backward.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
 lib.escort_plan_copy_tuning.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
 lib.escort_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+lib.escort_caffemodel_open.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+lib.escort_caffemodel_close.argtypes = [C.c_void_p]
+lib.escort_caffemodel_save.argtypes = [C.c_void_p, C.c_char_p]
+lib.escort_caffemodel_num_layers.argtypes = [C.c_void_p]
+lib.escort_caffemodel_find.argtypes = [C.c_void_p, C.c_char_p]
+lib.escort_caffemodel_layer.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+lib.escort_caffemodel_blob.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_long),
+                                       C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_long)]
 
 
 class EscortError(RuntimeError):
@@ -274,3 +284,62 @@ def measure_fp32_peak(variant=0, iters=4096):
     _check(lib.escort_measure_fp32_peak(variant, iters, C.byref(tf), C.byref(sms), C.byref(khz)),
            "escort_measure_fp32_peak")
     return tf.value, sms.value, khz.value
+
+
+class LayerInfo(C.Structure):
+    """escort_layer_info"""
+    _fields_ = [("name", C.c_char_p), ("type", C.c_char_p)] + [(n, C.c_int) for n in (
+        "num_blobs", "is_conv", "is_inner_product", "num_output", "bias_term", "group", "kernel_h", "kernel_w", "stride_h",
+        "stride_w", "pad_h", "pad_w", "dilation")]
+
+
+class CaffeModel:
+    """A `.caffemodel` opened through the C ABI (escort_caffemodel_*): what Net::CopyTrainedLayersFrom reads
+    (src/caffe/net.cpp:785-821).  Blob arrays are numpy views of the model's own host memory (writable: pruning)."""
+
+    def __init__(self, path):
+        h = C.c_void_p(0)
+        _check(lib.escort_caffemodel_open(path.encode(), C.byref(h)), "escort_caffemodel_open")
+        self.handle = h
+
+    def close(self):
+        if getattr(self, "handle", None):
+            lib.escort_caffemodel_close(self.handle)
+            self.handle = None
+
+    __del__ = close
+
+    def __len__(self):
+        return lib.escort_caffemodel_num_layers(self.handle)
+
+    def find(self, name):
+        return lib.escort_caffemodel_find(self.handle, name.encode())
+
+    def layer(self, i):
+        info = LayerInfo()
+        _check(lib.escort_caffemodel_layer(self.handle, i, C.byref(info)), "escort_caffemodel_layer")
+        d = {n: getattr(info, n) for n, _ in LayerInfo._fields_}
+        d["name"], d["type"] = info.name.decode(), info.type.decode()
+        return d
+
+    def blob(self, i, j):
+        import numpy as np
+        ndim, shape, data, count = C.c_int(0), (C.c_long * 8)(), C.POINTER(C.c_float)(), C.c_long(0)
+        _check(lib.escort_caffemodel_blob(self.handle, i, j, C.byref(ndim), shape, C.byref(data), C.byref(count)),
+               "escort_caffemodel_blob")
+        if count.value == 0:
+            return np.zeros(tuple(shape[:ndim.value]), dtype=np.float32)
+        return np.ctypeslib.as_array(data, shape=(count.value,)).reshape(tuple(shape[:ndim.value]))
+
+    def save(self, path):
+        _check(lib.escort_caffemodel_save(self.handle, path.encode()), "escort_caffemodel_save")
+
+
+def prune_magnitude(w, sparsity):
+    """In place on a C-contiguous float32 numpy array; returns (threshold, nnz)."""
+    import numpy as np
+    assert w.dtype == np.float32 and w.flags["C_CONTIGUOUS"]
+    thr, nnz = C.c_float(0), C.c_long(0)
+    _check(lib.escort_prune_magnitude(w.ctypes.data_as(C.POINTER(C.c_float)), C.c_long(w.size), C.c_double(sparsity),
+                                      C.byref(thr), C.byref(nnz)), "escort_prune_magnitude")
+    return thr.value, nnz.value

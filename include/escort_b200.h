@@ -165,6 +165,33 @@ ESCORT_API int escort_comm_unique_id(void *id128);
 ESCORT_API int escort_comm_init_rank(void **comm_out, int nranks, const void *id128, int rank);
 ESCORT_API int escort_comm_destroy(void *comm);
 
+/* ---- f4: weight on-disk path ------------------------------------------------------------------------------------
+ * Replaces Net::CopyTrainedLayersFrom(const string) (src/caffe/net.cpp:785-821: binary NetParameter -> per layer
+ * Blob::FromProto, src/caffe/blob.cpp:466-520 -> WeightAlign): a reader of the protobuf wire format for the fields of
+ * src/caffe/proto/caffe.proto that path touches (both `layer` = 100 and the V1 `layers` = 2), host memory only.
+ * Blob data pointers stay owned by the model and are writable, so a pruned model can be saved again. */
+typedef struct escort_caffemodel escort_caffemodel;
+typedef struct escort_layer_info {
+  const char *name, *type;          /* valid until close; V1 layers report their enum as "V1:<n>" */
+  int num_blobs, is_conv, is_inner_product;
+  int num_output, bias_term, group; /* ConvolutionParameter / InnerProductParameter, proto defaults when absent */
+  int kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation;
+} escort_layer_info;
+ESCORT_API int escort_caffemodel_open(const char *path, escort_caffemodel **out);
+ESCORT_API int escort_caffemodel_close(escort_caffemodel *m);
+ESCORT_API int escort_caffemodel_save(const escort_caffemodel *m, const char *path);
+ESCORT_API int escort_caffemodel_num_layers(const escort_caffemodel *m);
+/* index of the layer with this name (the match of net.cpp:790-796), or ESCORT_EINVAL */
+ESCORT_API int escort_caffemodel_find(const escort_caffemodel *m, const char *layer_name);
+ESCORT_API int escort_caffemodel_layer(const escort_caffemodel *m, int layer, escort_layer_info *info);
+/* blob `blob` of layer `layer` (0 = weights, 1 = bias): axes (legacy num/channels/height/width or shape.dim), data */
+ESCORT_API int escort_caffemodel_blob(escort_caffemodel *m, int layer, int blob, int *ndim, long *shape8, float **data_host,
+                                      long *count);
+/* magnitude pruning in place (host): the floor(count * sparsity) smallest |w| become 0.  The reference trains its
+ * sparsity with an L1 regulariser (src/caffe/solvers/sgd_solver.cpp:161-168) and ships pruned checkpoints (run.sh:13);
+ * this produces the same kind of input for WeightAlign from a dense checkpoint. */
+ESCORT_API int escort_prune_magnitude(float *weights_host, long count, double sparsity, float *threshold_out, long *nnz_out);
+
 /* ---- misc ---------------------------------------------------------------------------------------------------- */
 /* register-resident FFMA microbenchmark used for the FP32 roofline denominator;
  * returns achieved TFLOP/s in *tflops_host, SM count and SM clock (kHz, from device attributes). */

@@ -28,7 +28,7 @@ EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sco
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
            "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
-           "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
+           "escort_lowered_sparse_forward", "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
            "escort_caffemodel_find", "escort_caffemodel_layer", "escort_caffemodel_blob", "escort_prune_magnitude",
            "escort_last_error", "escort_version"]
 
@@ -284,6 +284,19 @@ def measure_fp32_peak(variant=0, iters=4096):
     _check(lib.escort_measure_fp32_peak(variant, iters, C.byref(tf), C.byref(sms), C.byref(khz)),
            "escort_measure_fp32_peak")
     return tf.value, sms.value, khz.value
+
+
+def lowered_sparse_forward(geom, bottom, csr_raw, bias=None, relu=False, stream=None):
+    """The LOWERED_SPARSE comparator (im2col + cusparseSpMM); csr_raw = weight_align(..., stretch=False)."""
+    num = bottom.shape[0]
+    Ho = out_dim(geom.height, geom.pad_h, geom.kernel_h, geom.stride_h, geom.dilation_h)
+    Wo = out_dim(geom.width, geom.pad_w, geom.kernel_w, geom.stride_w, geom.dilation_w)
+    col = torch.empty(geom.channels * geom.kernel_h * geom.kernel_w * Ho * Wo, device=bottom.device)
+    top = torch.empty((num, geom.num_output, Ho, Wo), device=bottom.device)
+    _check(lib.escort_lowered_sparse_forward(C.byref(geom), num, _ptr(bottom), _ptr(csr_raw["rowptr"]), _ptr(csr_raw["colidx"]),
+                                             _ptr(csr_raw["values"]), _ptr(bias), int(relu), _ptr(col), _ptr(top), _stream(stream)),
+           "escort_lowered_sparse_forward")
+    return top
 
 
 class LayerInfo(C.Structure):

@@ -165,6 +165,18 @@ ESCORT_API int escort_comm_unique_id(void *id128);
 ESCORT_API int escort_comm_init_rank(void **comm_out, int nranks, const void *id128, int rank);
 ESCORT_API int escort_comm_destroy(void *comm);
 
+/* ---- f3: the LOWERED_SPARSE comparator -----------------------------------------------------------------------------
+ * conv_mode 1 of the reference: per image im2col, then per group CSR x dense on cuSPARSE
+ * (BaseConvolutionLayer::forward_gpu_gemm, src/caffe/layers/base_conv_layer.cpp:715-745; caffe_gpu_sparse_csrmm =
+ * cusparseScsrmm2 + cublasSgeam, src/caffe/util/math_functions.cu:48-62 -- csrmm2 no longer exists, this runs
+ * cusparseSpMM), bias as forward_gpu_bias.  rowptr / colidx / values in the reference's blob layout with RAW column
+ * indices ((ic * kh + r) * kw + s: WeightAlign without the stretch).  `col_buffer`: group * (C/group) * kh * kw * Ho * Wo
+ * floats of scratch (col_buffer_).  Unlike the reference, no density gate: the sparse product always runs.
+ * A comparator for the paper's "cuSPARSE" baseline, not a product path; needs libcusparse.so.12 at run time. */
+ESCORT_API int escort_lowered_sparse_forward(const escort_geom *geom, int num, const float *bottom, const int *rowptr,
+                                             const int *colidx_raw, const float *values, const float *bias, int fuse_relu,
+                                             float *col_buffer, float *top, escort_stream_t stream);
+
 /* ---- f4: weight on-disk path ------------------------------------------------------------------------------------
  * Replaces Net::CopyTrainedLayersFrom(const string) (src/caffe/net.cpp:785-821: binary NetParameter -> per layer
  * Blob::FromProto, src/caffe/blob.cpp:466-520 -> WeightAlign): a reader of the protobuf wire format for the fields of

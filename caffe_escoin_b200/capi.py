@@ -28,7 +28,7 @@ EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sco
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
            "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
-           "escort_lowered_sparse_forward", "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
+           "escort_bn_scale_to_affine", "escort_plan_fold_affine", "escort_lowered_sparse_forward", "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
            "escort_caffemodel_find", "escort_caffemodel_layer", "escort_caffemodel_blob", "escort_prune_magnitude",
            "escort_last_error", "escort_version"]
 
@@ -284,6 +284,23 @@ def measure_fp32_peak(variant=0, iters=4096):
     _check(lib.escort_measure_fp32_peak(variant, iters, C.byref(tf), C.byref(sms), C.byref(khz)),
            "escort_measure_fp32_peak")
     return tf.value, sms.value, khz.value
+
+
+def bn_scale_to_affine(mean, var, scale_factor_blob, eps, gamma=None, beta=None, stream=None):
+    """(a, b) of y = x * a + b for BatchNorm(use_global_stats) followed by Scale (device tensors of num_output floats)."""
+    a, b = torch.empty_like(mean), torch.empty_like(mean)
+    _check(lib.escort_bn_scale_to_affine(mean.numel(), _ptr(mean), _ptr(var), C.c_float(scale_factor_blob), C.c_float(eps), _ptr(gamma),
+                                         _ptr(beta), _ptr(a), _ptr(b), _stream(stream)), "escort_bn_scale_to_affine")
+    return a, b
+
+
+def fold_affine(plan, weights_dense, a, b, bias=None, stream=None):
+    """Fold y = conv * a[oc] + b[oc] into the plan; returns the bias to pass to plan.forward(..., relu=True)."""
+    wf = torch.empty_like(weights_dense)
+    bias_out = torch.empty_like(a)
+    _check(lib.escort_plan_fold_affine(plan.h, _ptr(weights_dense), _ptr(a), _ptr(b), _ptr(bias), _ptr(wf), _ptr(bias_out),
+                                       _stream(stream)), "escort_plan_fold_affine")
+    return bias_out
 
 
 def lowered_sparse_forward(geom, bottom, csr_raw, bias=None, relu=False, stream=None):

@@ -799,3 +799,62 @@ extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense,
   if (p->tile || p->tm) return tile_refresh(p, weights_dense, stream);
   return 0;
 }
+
+// ---- f2: glue-layer fusion ------------------------------------------------------------------------------------
+// conv -> BatchNorm (use_global_stats) -> Scale -> ReLU is the chain every ResNet-50 branch2b conv sits in; the reference
+// runs four layers and four passes over the activation (net.cpp:531-532 counts them as "other time").  At inference
+// the BatchNorm + Scale pair is one affine map per output channel, y = conv * a[oc] + b[oc], and that folds into the
+// plan: the nonzero weights of row oc are multiplied by a[oc] (positions, hence the mask and every kernel's record
+// stream, are unchanged) and the bias becomes bias * a + b.  The forward launch with fuse_relu then IS the whole chain:
+// no extra kernel, no extra byte of HBM traffic.
+__global__ void bn_scale_affine_kernel(int M, const float *__restrict__ mean, const float *__restrict__ var, float scale_factor, float eps,
+                                       const float *__restrict__ gamma, const float *__restrict__ beta, float *__restrict__ a,
+                                       float *__restrict__ b) {
+  const int oc = blockIdx.x * blockDim.x + threadIdx.x;
+  if (oc >= M) return;
+  // BatchNormLayer::Forward with use_global_stats (src/caffe/layers/batch_norm_layer.cpp:98-106, 139-152):
+  // mean = blobs[0] * sf, variance = blobs[1] * sf, top = (x - mean) / sqrt(variance + eps); then ScaleLayer: * gamma + beta
+  const float m = mean[oc] * scale_factor, v = var[oc] * scale_factor;
+  const float inv = 1.0f / sqrtf(v + eps);
+  const float g = gamma ? gamma[oc] : 1.0f;
+  a[oc] = g * inv;
+  b[oc] = (beta ? beta[oc] : 0.0f) - m * inv * g;
+}
+
+__global__ void fold_affine_kernel(long total, long row, int M, const float *__restrict__ w, const float *__restrict__ a,
+                                   const float *__restrict__ b, const float *__restrict__ bias_in, float *__restrict__ w_out,
+                                   float *__restrict__ bias_out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < total) w_out[e] = w[e] * __ldg(a + e / row);
+  if (e < M && bias_out) bias_out[e] = (bias_in ? bias_in[e] : 0.0f) * a[e] + (b ? b[e] : 0.0f);
+}
+
+extern "C" int escort_bn_scale_to_affine(int num_output, const float *bn_mean, const float *bn_var, float bn_scale_factor_blob, float eps,
+                                         const float *scale_gamma, const float *scale_beta, float *a_out, float *b_out,
+                                         escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(num_output > 0 && bn_mean && bn_var && a_out && b_out, "escort_bn_scale_to_affine: bad arguments");
+  const float sf = bn_scale_factor_blob == 0.f ? 0.f : 1.f / bn_scale_factor_blob;  // batch_norm_layer.cpp:100-101
+  bn_scale_affine_kernel<<<(num_output + 127) / 128, 128, 0, stream>>>(num_output, bn_mean, bn_var, sf, eps, scale_gamma, scale_beta, a_out,
+                                                                        b_out);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int escort_plan_fold_affine(escort_plan *p, const float *weights_dense, const float *a, const float *b, const float *bias_in,
+                                       float *weights_folded, float *bias_out, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(p && weights_dense && a && weights_folded, "escort_plan_fold_affine: bad arguments");
+  const escort_geom &g = p->g;
+  const long row = (long)(g.channels / g.group) * g.kernel_h * g.kernel_w, total = row * g.num_output;
+  const long threads = std::max<long>(total, g.num_output);
+  fold_affine_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(total, row, g.num_output, weights_dense, a, b, bias_in, weights_folded,
+                                                                           bias_out);
+  ESCORT_LAUNCH_CHECK();
+  // an inference-time refresh: do not build the backward sub-plan for it
+  const int tried = p->bwd_tried;
+  if (!p->bwd) p->bwd_tried = 1;
+  const int rc = escort_refresh_values(p, weights_folded, nullptr, stream_);
+  p->bwd_tried = tried;
+  return rc;
+}

@@ -165,6 +165,21 @@ ESCORT_API int escort_comm_unique_id(void *id128);
 ESCORT_API int escort_comm_init_rank(void **comm_out, int nranks, const void *id128, int rank);
 ESCORT_API int escort_comm_destroy(void *comm);
 
+/* ---- f2: glue-layer fusion ------------------------------------------------------------------------------------------
+ * conv -> BatchNorm(use_global_stats) -> Scale -> ReLU (the chain around every ResNet-50 sparse conv; the reference runs
+ * four layers, src/caffe/net.cpp:531-532 "other time") as ONE forward launch: the per-channel affine
+ * y = conv * a[oc] + b[oc] is folded into the plan's nonzero weights (the mask and every record stream keep their
+ * positions) and into the bias.  escort_bn_scale_to_affine turns the reference's blobs into (a, b):
+ * BatchNormLayer blobs {mean, variance, scale_factor} (src/caffe/layers/batch_norm_layer.cpp:98-106, 139-152) and
+ * ScaleLayer blobs {gamma, beta} (may be NULL).  escort_plan_fold_affine: weights_folded = W * a[oc] (dense scratch the
+ * caller owns, same size as the weight blob), bias_out = bias_in * a + b, then the plan is refreshed from weights_folded;
+ * afterwards escort_sconv_forward(plan, ..., bias_out, fuse_relu = 1, ...) is the whole chain.  All pointers device. */
+ESCORT_API int escort_bn_scale_to_affine(int num_output, const float *bn_mean, const float *bn_var, float bn_scale_factor_blob, float eps,
+                                         const float *scale_gamma, const float *scale_beta, float *a_out, float *b_out,
+                                         escort_stream_t stream);
+ESCORT_API int escort_plan_fold_affine(escort_plan *plan, const float *weights_dense, const float *a, const float *b,
+                                       const float *bias_in, float *weights_folded, float *bias_out, escort_stream_t stream);
+
 /* ---- f3: the LOWERED_SPARSE comparator -----------------------------------------------------------------------------
  * conv_mode 1 of the reference: per image im2col, then per group CSR x dense on cuSPARSE
  * (BaseConvolutionLayer::forward_gpu_gemm, src/caffe/layers/base_conv_layer.cpp:715-745; caffe_gpu_sparse_csrmm =

@@ -28,6 +28,7 @@ EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sco
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
            "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
+           "escort_inner_product_forward", "escort_dense_conv_workspace_bytes", "escort_dense_conv_forward",
            "escort_bn_scale_to_affine", "escort_plan_fold_affine", "escort_lowered_sparse_forward", "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
            "escort_caffemodel_find", "escort_caffemodel_layer", "escort_caffemodel_blob", "escort_prune_magnitude",
            "escort_last_error", "escort_version"]
@@ -284,6 +285,31 @@ def measure_fp32_peak(variant=0, iters=4096):
     _check(lib.escort_measure_fp32_peak(variant, iters, C.byref(tf), C.byref(sms), C.byref(khz)),
            "escort_measure_fp32_peak")
     return tf.value, sms.value, khz.value
+
+
+lib.escort_dense_conv_workspace_bytes.restype = C.c_size_t
+
+
+def inner_product_forward(bottom, weight, bias=None, relu=False, stream=None):
+    """InnerProduct forward on tcgen05 (TF32): bottom [num x K], weight [num_output x K]."""
+    num, K = bottom.shape
+    top = torch.empty((num, weight.shape[0]), device=bottom.device)
+    _check(lib.escort_inner_product_forward(num, K, weight.shape[0], _ptr(bottom), _ptr(weight), _ptr(bias), int(relu), _ptr(top),
+                                            _stream(stream)), "escort_inner_product_forward")
+    return top
+
+
+def dense_conv_forward(geom, bottom, weight, bias=None, relu=False, stream=None):
+    """Dense convolution (conv1 / 1x1 / unpruned) on tcgen05 (TF32): transposed im2col + GEMM."""
+    num = bottom.shape[0]
+    Ho = out_dim(geom.height, geom.pad_h, geom.kernel_h, geom.stride_h, geom.dilation_h)
+    Wo = out_dim(geom.width, geom.pad_w, geom.kernel_w, geom.stride_w, geom.dilation_w)
+    nbytes = lib.escort_dense_conv_workspace_bytes(C.byref(geom), num)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=bottom.device)
+    top = torch.empty((num, geom.num_output, Ho, Wo), device=bottom.device)
+    _check(lib.escort_dense_conv_forward(C.byref(geom), num, _ptr(bottom), _ptr(weight), _ptr(bias), int(relu), _ptr(ws), C.c_size_t(nbytes),
+                                         _ptr(top), _stream(stream)), "escort_dense_conv_forward")
+    return top
 
 
 def bn_scale_to_affine(mean, var, scale_factor_blob, eps, gamma=None, beta=None, stream=None):

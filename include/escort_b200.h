@@ -165,6 +165,21 @@ ESCORT_API int escort_comm_unique_id(void *id128);
 ESCORT_API int escort_comm_init_rank(void **comm_out, int nranks, const void *id128, int rank);
 ESCORT_API int escort_comm_destroy(void *comm);
 
+/* ---- f1: the layers the reference keeps dense, on tcgen05 ----------------------------------------------------------
+ * InnerProductLayer::Forward_gpu (src/caffe/layers/inner_product_layer.cu:9-31, cuBLAS sgemm + bias gemv):
+ * top[num x num_output] = bottom[num x K] * weight[num_output x K]^T + bias, optional ReLU, and
+ * EscConvolutionLayer::Forward_gpu (src/caffe/layers/esc_conv_layer.cu:21-29, cuDNN IMPLICIT_GEMM) for conv1 / 1x1 /
+ * unpruned convolutions: one TMA + tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) GEMM kernel, fused bias / ReLU
+ * epilogue.  TF32 products: ~5e-4 relative L2 against fp32 (the sparse path's 1e-4 bar is for the sparse path).
+ * inner product: K % 4 == 0, operands 16-byte aligned.  conv: group == 1; `workspace` (device) holds the padded weights
+ * and the transposed column buffer, escort_dense_conv_workspace_bytes(geom, num) bytes. */
+ESCORT_API int escort_inner_product_forward(int num, int K, int num_output, const float *bottom, const float *weight,
+                                            const float *bias, int fuse_relu, float *top, escort_stream_t stream);
+ESCORT_API size_t escort_dense_conv_workspace_bytes(const escort_geom *geom, int num);
+ESCORT_API int escort_dense_conv_forward(const escort_geom *geom, int num, const float *bottom, const float *weight,
+                                         const float *bias, int fuse_relu, void *workspace, size_t workspace_bytes, float *top,
+                                         escort_stream_t stream);
+
 /* ---- f2: glue-layer fusion ------------------------------------------------------------------------------------------
  * conv -> BatchNorm(use_global_stats) -> Scale -> ReLU (the chain around every ResNet-50 sparse conv; the reference runs
  * four layers, src/caffe/net.cpp:531-532 "other time") as ONE forward launch: the per-channel affine

@@ -52,6 +52,13 @@ CONV_CASES = [  # name, N, Cin, Cout, H, k, stride, pad
     ("pointwise_reduce", 5, 96, 40, 14, 1, 1, 0),
     ("pointwise_wide", 2, 64, 256, 28, 1, 1, 0),
     ("dense_3x3", 4, 20, 130, 13, 3, 1, 1),
+    # 1x1 / stride 1: the implicit GEMM straight from NCHW (MN-major A operand); ragged K, N and pixel tails
+    ("pointwise_k36_m300", 3, 36, 300, 14, 1, 1, 0),
+    ("pointwise_small_map", 2, 128, 64, 8, 1, 1, 0),
+    ("pointwise_deep_k", 2, 544, 96, 12, 1, 1, 0),
+    # 1x1 shapes the implicit GEMM does not take (odd pixel count, stride 2): column-buffer path
+    ("pointwise_7px", 2, 64, 48, 7, 1, 1, 0),
+    ("pointwise_stride2", 2, 32, 48, 14, 1, 2, 0),
 ]
 
 
@@ -73,3 +80,22 @@ def test_dense_conv(case):
     torch.cuda.synchronize()
     assert y.shape == ref.shape
     assert po.rel_l2(y.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.gpu
+def test_pointwise_implicit_gemm_matches_column_buffer_path(monkeypatch):
+    """The same layer through both dense-conv paths (ESCORT_DENSE_NO_IMPLICIT forces the column buffer), without bias / ReLU."""
+    import torch
+    from caffe_escoin_b200 import capi
+    rng = np.random.default_rng(5)
+    x = torch.from_numpy(rng.uniform(-1, 1, (3, 72, 10, 10)).astype(np.float32)).cuda()
+    w = torch.from_numpy((rng.standard_normal((136, 72, 1, 1)) / np.sqrt(72)).astype(np.float32)).cuda()
+    geom = capi.make_geom(72, 136, 10, 10, 1, 1, 0, 1, 1)
+    y_imp = capi.dense_conv_forward(geom, x, w, None, relu=False)
+    monkeypatch.setenv("ESCORT_DENSE_NO_IMPLICIT", "1")
+    y_col = capi.dense_conv_forward(geom, x, w, None, relu=False)
+    torch.cuda.synchronize()
+    ref = torch.einsum("nchw,mc->nmhw", x.double(), w.double()[:, :, 0, 0])
+    assert float((y_imp.double() - ref).norm() / ref.norm()) < TOL
+    assert float((y_col.double() - ref).norm() / ref.norm()) < TOL
+    assert float((y_imp - y_col).norm() / y_col.norm()) < TOL

@@ -46,10 +46,13 @@ for name, K, M in [("alexnet/fc6", 9216, 4096), ("alexnet/fc7", 4096, 4096), ("a
     print("  %-20s K %5d M %5d | tcgen05 tf32 %7.3f ms %7.1f TFLOP/s rel_l2 %.1e | cuBLAS fp32 %7.3f ms %6.1f | cuBLAS tf32 %7.3f ms %6.1f"
           % (name, K, M, t, fl / t / 1e9, err, t32, fl / t32 / 1e9, ttf, fl / ttf / 1e9), flush=True)
 
-print("dense convolution (EscConvolutionLayer::Forward_gpu, batch %d; ours = transposed im2col + GEMM, incl. both)" % N)
+print("dense convolution (EscConvolutionLayer::Forward_gpu, batch %d; ours = implicit GEMM from NCHW for 1x1 / stride 1, else "
+      "transposed im2col + GEMM, both kernels timed; GB/s = (bottom + top bytes) / time)" % N)
 for name, Cin, Cout, H, k, s, p in [("alexnet/conv1", 3, 96, 227, 11, 4, 0), ("googlenet/conv1", 3, 64, 224, 7, 2, 3),
                                    ("googlenet/conv2_reduce", 64, 64, 56, 1, 1, 0), ("resnet50/res2a_branch2a", 64, 64, 56, 1, 1, 0),
-                                   ("resnet50/res2a_branch2c", 64, 256, 56, 1, 1, 0), ("resnet50/res4a_branch2a", 512, 256, 14, 1, 1, 0),
+                                   ("resnet50/res2a_branch2c", 64, 256, 56, 1, 1, 0), ("resnet50/res2b_branch2a", 256, 64, 56, 1, 1, 0),
+                                   ("resnet50/res3a_branch2c", 128, 512, 28, 1, 1, 0), ("resnet50/res4a_branch2a", 512, 256, 14, 1, 1, 0),
+                                   ("resnet50/res4a_branch2c", 256, 1024, 14, 1, 1, 0), ("resnet50/res4b_branch2a", 1024, 256, 14, 1, 1, 0),
                                    ("resnet50/res5a_branch2c", 512, 2048, 7, 1, 1, 0)]:
     x = torch.rand(N, Cin, H, H, device="cuda") - 0.5
     w = (torch.rand(Cout, Cin, k, k, device="cuda") - 0.5) / (Cin * k * k) ** 0.5
@@ -64,5 +67,6 @@ for name, Cin, Cout, H, k, s, p in [("alexnet/conv1", 3, 96, 227, 11, 4, 0), ("g
     torch.backends.cudnn.allow_tf32 = False
     ref = conv()
     err = float((capi.dense_conv_forward(geom, x, w, b, relu=True) - ref).norm() / ref.norm())
-    print("  %-26s | tcgen05 tf32 %7.3f ms %7.1f TFLOP/s rel_l2 %.1e | cuDNN fp32 %7.3f ms %6.1f | cuDNN tf32 %7.3f ms %6.1f"
-          % (name, t, fl / t / 1e9, err, t32, fl / t32 / 1e9, ttf, fl / ttf / 1e9), flush=True)
+    gbs = 4.0 * N * (Cin * H * H + Cout * Ho * Ho) / t / 1e6
+    print("  %-26s | tcgen05 tf32 %7.3f ms %7.1f TFLOP/s %5.0f GB/s rel_l2 %.1e | cuDNN fp32 %7.3f ms %6.1f | cuDNN tf32 %7.3f ms %6.1f"
+          % (name, t, fl / t / 1e9, gbs, err, t32, fl / t32 / 1e9, ttf, fl / ttf / 1e9), flush=True)

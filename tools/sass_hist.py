@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """SASS opcode histogram of the kernels in libescort_b200.so (cuobjdump -sass), one line per kernel: the mnemonics that
-tell which hardware path a kernel uses (LDTM / STTM = tcgen05.ld / st, UTMALDG = TMA tensor load, LDGSTS = cp.async,
+tell which hardware path a kernel uses (UTCHMMA = tcgen05.mma kind::tf32, UTCBAR = tcgen05.commit, LDTM / STTM = tcgen05.ld / st, UTMALDG = TMA tensor load, LDGSTS = cp.async,
 SYNCS = mbarrier, FFMA2 = packed fp32 FMA, USETMAXREG = setmaxnreg).  python tools/sass_hist.py [regex] > profiles/..."""
 import os
 import re
@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = os.path.join(ROOT, "caffe_escoin_b200", "libescort_b200.so")
 pat = re.compile(sys.argv[1]) if len(sys.argv) > 1 else None
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
-KEYS = ["FFMA2", "FFMA", "LDTM", "STTM", "UTMALDG", "LDGSTS", "SYNCS", "BAR", "USETMAXREG", "LDS", "STS", "STG", "ATOMG", "RED", "SHFL", "R2UR", "BRA"]
+KEYS = ["FFMA2", "FFMA", "UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "LDGSTS", "SYNCS", "BAR", "USETMAXREG", "LDS", "STS", "STG", "ATOMG", "RED", "SHFL", "R2UR", "BRA"]
 name, cnt, rows = None, Counter(), []
 
 

@@ -169,10 +169,12 @@ ESCORT_API int escort_comm_destroy(void *comm);
  * InnerProductLayer::Forward_gpu (src/caffe/layers/inner_product_layer.cu:9-31, cuBLAS sgemm + bias gemv):
  * top[num x num_output] = bottom[num x K] * weight[num_output x K]^T + bias, optional ReLU, and
  * EscConvolutionLayer::Forward_gpu (src/caffe/layers/esc_conv_layer.cu:21-29, cuDNN IMPLICIT_GEMM) for conv1 / 1x1 /
- * unpruned convolutions: one TMA + tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) GEMM kernel, fused bias / ReLU
- * epilogue.  TF32 products: ~5e-4 relative L2 against fp32 (the sparse path's 1e-4 bar is for the sparse path).
- * inner product: K % 4 == 0, operands 16-byte aligned.  conv: group == 1; `workspace` (device) holds the padded weights
- * and the transposed column buffer, escort_dense_conv_workspace_bytes(geom, num) bytes. */
+ * unpruned convolutions: TMA + tcgen05.mma (kind::tf32, fp32 accumulate in TMEM) GEMM kernels, fused bias / ReLU
+ * epilogue.  TF32 products: up to 7e-4 relative L2 against fp32 (the sparse path's 1e-4 bar is for the sparse path).
+ * inner product: K % 4 == 0, operands 16-byte aligned.  conv: group == 1.  1x1 / stride 1 / no-padding layers whose
+ * pixel count and channel count are multiples of 4 run as an implicit GEMM straight from NCHW; every other geometry
+ * goes through `workspace` (device): the padded weights and the transposed column buffer,
+ * escort_dense_conv_workspace_bytes(geom, num) bytes (always required, so that the caller need not know which path runs). */
 ESCORT_API int escort_inner_product_forward(int num, int K, int num_output, const float *bottom, const float *weight,
                                             const float *bias, int fuse_relu, float *top, escort_stream_t stream);
 ESCORT_API size_t escort_dense_conv_workspace_bytes(const escort_geom *geom, int num);

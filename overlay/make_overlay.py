@@ -180,6 +180,58 @@ def _(t):
     return t
 
 
+# ---- the layers the reference keeps dense, on tcgen05 (TF32 products, fp32 accumulate) ----
+@edit("src/caffe/layers/inner_product_layer.cu")
+def _(t):
+    return insert_before(t, "  if (M_ == 1) {\n    caffe_gpu_gemv<Dtype>(CblasNoTrans, N_, K_, (Dtype)1.,\n                         weight, bottom_data, (Dtype)0., top_data);",
+                         """  if (sizeof(Dtype) == sizeof(float) && !transpose_ && M_ > 1 && K_ % 4 == 0) {
+    // escort-b200: one tcgen05 GEMM (TMA-staged operands, TMEM accumulator) with the bias fused, instead of sgemm + rank-1 bias GEMM
+    ESCORT_CHECK(escort_inner_product_forward(M_, K_, N_, reinterpret_cast<const float*>(bottom_data),
+        reinterpret_cast<const float*>(weight),
+        bias_term_ ? reinterpret_cast<const float*>(this->blobs_[1]->gpu_data()) : NULL, /*fuse_relu=*/0,
+        reinterpret_cast<float*>(top_data), NULL));
+    return;
+  }
+""")
+
+
+@edit("include/caffe/layers/esc_conv_layer.hpp")
+def _(t):
+    t = t.replace(": BaseConvolutionLayer<Dtype>(param), handles_setup_(false) {}",
+                  ": BaseConvolutionLayer<Dtype>(param), handles_setup_(false), escort_ws_(NULL), escort_ws_bytes_(0) {}")
+    return insert_after(t, "  void **workspace;  // aliases into workspaceData\n",
+                        "  void *escort_ws_;  // escort-b200: column buffer of the tcgen05 path (unused by 1x1 layers)\n  size_t escort_ws_bytes_;\n")
+
+
+@edit("src/caffe/layers/esc_conv_layer.cpp")
+def _(t):
+    return insert_after(t, "EscConvolutionLayer<Dtype>::~EscConvolutionLayer() {\n", "  cudaFree(escort_ws_);  // escort-b200\n")
+
+
+@edit("src/caffe/layers/esc_conv_layer.cu")
+def _(t):
+    return insert_after(t, "    Dtype* top_data = top[i]->mutable_gpu_data();\n", """    if (sizeof(Dtype) == sizeof(float) && this->group_ == 1) {
+      // escort-b200: tcgen05 convolution, bias fused -- an implicit GEMM straight from NCHW for 1x1 / stride 1 layers,
+      // a transposed column buffer for conv1-type layers -- instead of cuDNN IMPLICIT_GEMM + cudnnAddTensor
+      escort_geom eg = {this->channels_, this->num_output_, 1, bottom[i]->height(), bottom[i]->width(),
+          this->kernel_shape_.cpu_data()[0], this->kernel_shape_.cpu_data()[1],
+          this->pad_.cpu_data()[0], this->pad_.cpu_data()[1], this->stride_.cpu_data()[0], this->stride_.cpu_data()[1],
+          this->dilation_.cpu_data()[0], this->dilation_.cpu_data()[1]};
+      const size_t need = escort_dense_conv_workspace_bytes(&eg, this->num_);
+      if (need > escort_ws_bytes_) {
+        cudaFree(escort_ws_);
+        CUDA_CHECK(cudaMalloc(&escort_ws_, need));
+        escort_ws_bytes_ = need;
+      }
+      ESCORT_CHECK(escort_dense_conv_forward(&eg, this->num_, reinterpret_cast<const float*>(bottom_data),
+          reinterpret_cast<const float*>(weight),
+          this->bias_term_ ? reinterpret_cast<const float*>(this->blobs_[1]->gpu_data()) : NULL, /*fuse_relu=*/0,
+          escort_ws_, escort_ws_bytes_, reinterpret_cast<float*>(top_data), NULL));
+      continue;
+    }
+""")
+
+
 @edit("Makefile")
 def _(t):
     return insert_after(t, "LIBRARIES += glog gflags protobuf boost_system boost_filesystem m hdf5_hl hdf5 spmp\n",

@@ -27,6 +27,11 @@ EXPECT = {
     "src/caffe/parallel.cpp": ["escort_allreduce_grads(comm_"],
     "include/caffe/util/device_alternate.hpp": ["#define ESCORT_CHECK(call)"],
     "Makefile": ["LIBRARIES += escort_b200"],
+    # the dense layers
+    "src/caffe/layers/inner_product_layer.cu": ["escort_inner_product_forward(M_, K_, N_"],
+    "src/caffe/layers/esc_conv_layer.cu": ["escort_dense_conv_workspace_bytes(&eg", "escort_dense_conv_forward(&eg"],
+    "src/caffe/layers/esc_conv_layer.cpp": ["cudaFree(escort_ws_)"],
+    "include/caffe/layers/esc_conv_layer.hpp": ["void *escort_ws_;", "escort_ws_bytes_(0)"],
 }
 
 

@@ -319,15 +319,16 @@ def run_train_leg(args, world, rank, torch, dist, capi, wl, barrier):
     ev_bwd = torch.cuda.Event(enable_timing=True)
     ev_all = torch.cuda.Event(enable_timing=True)
 
-    def step(mark=False):
+    def step(mark=False, layerwise=True):
         for L in layers:
             L["plan"].forward(L["x"], L["b"], relu=False, top=L["y"])
         for L in reversed(layers):
             L["plan"].backward_weight(L["x"], L["dy"], wd_csr=L["wd"], accumulate=False)
             if L["db"] is not None:
                 capi.bias_backward(L["dy"], L["db"])
-            if comm is not None:
+            if comm is not None and layerwise:
                 # this layer's gradient is final: reduce it on the side stream while the next layers' backward runs
+                # (solver param layer_wise_reduce: true -> NCCL::run(layer), parallel.cpp:202-235)
                 e = torch.cuda.Event()
                 e.record(main)
                 side.wait_event(e)
@@ -336,21 +337,43 @@ def run_train_leg(args, world, rank, torch, dist, capi, wl, barrier):
         if mark:
             ev_bwd.record(main)
         if comm is not None:
-            main.wait_stream(side)
+            if layerwise:
+                main.wait_stream(side)
+            else:
+                # layer_wise_reduce: false -> one all-reduce of the flat diff buffer (on_gradients_ready, parallel.cpp:246-255)
+                capi.allreduce_grads(flat, 1.0 / world, comm)
         if mark:
             ev_all.record(main)
+
+    def timed(n, layerwise, mark_last=False):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s in range(n):
+            step(mark=(mark_last and s == n - 1), layerwise=layerwise)
+        t1.record()
+        barrier()
+        ms_ = t0.elapsed_time(t1) / n
+        if world > 1:
+            t = torch.tensor([ms_], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_ = float(t[0].item())
+        return ms_
 
     steps, warm = 3, 2
     for _ in range(warm):
         step()
-    barrier()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for s in range(steps):
-        step(mark=(s == steps - 1))
-    t1.record()
-    barrier()
-    ms = t0.elapsed_time(t1) / steps
+    # Both of the reference's exchange modes are measured (2 steps each, max over ranks) and the faster one is timed:
+    # the CSR-ordered gradients are small (13.6 MB for the 16 layers), and a persistent compute kernel that finds an SM
+    # taken by an NCCL kernel runs one CTA late, so "overlap" can cost more than the flat exchange it hides.
+    mode_ms = {"layerwise": None, "flat": None}
+    layerwise = True
+    if comm is not None:
+        step(layerwise=False)
+        mode_ms["layerwise"] = timed(2, True)
+        mode_ms["flat"] = timed(2, False)
+        layerwise = mode_ms["layerwise"] <= mode_ms["flat"]
+    ms = timed(steps, layerwise, mark_last=True)
     exposed = ev_bwd.elapsed_time(ev_all)
     # the exchange alone (same buffers, nothing to overlap with): bus bandwidth of the flat all-reduce
     bus = None
@@ -367,9 +390,9 @@ def run_train_leg(args, world, rank, torch, dist, capi, wl, barrier):
         exch_ms = e0.elapsed_time(e1) / 5
         bus = 2.0 * (world - 1) / world * flat.numel() * 4 / (exch_ms * 1e-3) / 1e9
     if world > 1:
-        t = torch.tensor([ms, exposed], device="cuda")
+        t = torch.tensor([exposed], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, exposed = float(t[0].item()), float(t[1].item())
+        exposed = float(t[0].item())
     parity, worst = check_parity(layers, True, torch, capi) if rank == 0 else ({}, 0.0)
     if comm is not None:
         torch.cuda.synchronize()
@@ -377,8 +400,11 @@ def run_train_leg(args, world, rank, torch, dist, capi, wl, barrier):
     flops = sum(L["flops"] for L in layers) * 3
     return {"workload": "resnet50_branch2b_3x3_pruned70_fwd+masked-bwd_b256", "value": world * N / (ms * 1e-3), "unit": UNIT,
             "ms_per_step": ms, "steps": steps, "warmup": warm, "tflops": flops / ms / 1e9,
-            "exchange": {"through": "escort_allreduce_grads(ncclComm_t) per layer on a side stream, 1/N fused behind it"
+            "exchange": {"through": ("escort_allreduce_grads(ncclComm_t) " + ("per layer on a side stream" if layerwise else
+                                     "once on the flat CSR-ordered diff buffer after the backward") + ", 1/N fused behind it")
                                     if comm is not None else "single rank: no exchange",
+                         "mode": ("layerwise" if layerwise else "flat") if comm is not None else None,
+                         "mode_ms_per_step": mode_ms,
                          "allreduce_bytes_per_step": flat.numel() * 4 if comm is not None else 0,
                          "exposed_ms": exposed if comm is not None else 0.0,
                          "standalone_ms": exch_ms, "bus_gbs": bus},

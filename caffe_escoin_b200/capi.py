@@ -28,7 +28,7 @@ EXPORTS = ["escort_pack_csr", "escort_stretch", "escort_copy_input", "escort_sco
            "escort_sconv_forward", "escort_sconv_backward_data", "escort_sconv_backward_weight",
            "escort_bias_backward", "escort_refresh_values", "escort_allreduce_grads", "escort_broadcast",
            "escort_comm_unique_id", "escort_comm_init_rank", "escort_comm_destroy", "escort_tmem_debug", "escort_measure_fp32_peak",
-           "escort_inner_product_forward", "escort_dense_conv_workspace_bytes", "escort_dense_conv_forward",
+           "escort_inner_product_forward", "escort_dense_conv_workspace_bytes", "escort_dense_conv_forward", "escort_dense_conv_forward_residual", "escort_dense_fold_affine",
            "escort_bn_scale_to_affine", "escort_plan_fold_affine", "escort_lowered_sparse_forward", "escort_caffemodel_open", "escort_caffemodel_close", "escort_caffemodel_save", "escort_caffemodel_num_layers",
            "escort_caffemodel_find", "escort_caffemodel_layer", "escort_caffemodel_blob", "escort_prune_magnitude",
            "escort_last_error", "escort_version"]
@@ -147,7 +147,7 @@ class Plan:
         self.h = h
 
     def __del__(self):
-        if getattr(self, "h", None):
+        if getattr(self, "h", None) and lib is not None:   # (module globals are gone at interpreter shutdown)
             lib.escort_plan_destroy(self.h)
             self.h = None
 
@@ -299,17 +299,35 @@ def inner_product_forward(bottom, weight, bias=None, relu=False, stream=None):
     return top
 
 
-def dense_conv_forward(geom, bottom, weight, bias=None, relu=False, stream=None):
-    """Dense convolution (conv1 / 1x1 / unpruned) on tcgen05 (TF32): transposed im2col + GEMM."""
+def dense_conv_forward(geom, bottom, weight, bias=None, relu=False, stream=None, residual=None, top=None, workspace=None):
+    """Dense convolution (conv1 / 1x1 / unpruned) on tcgen05 (TF32): implicit GEMM from NCHW for 1x1 / stride 1, else
+    transposed im2col + GEMM.  residual: the other input of the Eltwise SUM behind the layer (fused into the epilogue)."""
     num = bottom.shape[0]
     Ho = out_dim(geom.height, geom.pad_h, geom.kernel_h, geom.stride_h, geom.dilation_h)
     Wo = out_dim(geom.width, geom.pad_w, geom.kernel_w, geom.stride_w, geom.dilation_w)
     nbytes = lib.escort_dense_conv_workspace_bytes(C.byref(geom), num)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=bottom.device)
-    top = torch.empty((num, geom.num_output, Ho, Wo), device=bottom.device)
-    _check(lib.escort_dense_conv_forward(C.byref(geom), num, _ptr(bottom), _ptr(weight), _ptr(bias), int(relu), _ptr(ws), C.c_size_t(nbytes),
-                                         _ptr(top), _stream(stream)), "escort_dense_conv_forward")
+    ws = workspace if workspace is not None else torch.empty(nbytes, dtype=torch.uint8, device=bottom.device)
+    assert ws.numel() * ws.element_size() >= nbytes
+    if top is None:
+        top = torch.empty((num, geom.num_output, Ho, Wo), device=bottom.device)
+    _check(lib.escort_dense_conv_forward_residual(C.byref(geom), num, _ptr(bottom), _ptr(weight), _ptr(bias), _ptr(residual), int(relu),
+                                                  _ptr(ws), C.c_size_t(nbytes), _ptr(top), _stream(stream)),
+           "escort_dense_conv_forward_residual")
     return top
+
+
+def dense_conv_workspace_bytes(geom, num):
+    return int(lib.escort_dense_conv_workspace_bytes(C.byref(geom), num))
+
+
+def dense_fold_affine(weights, a, b, bias=None, stream=None):
+    """W'[oc] = W[oc] * a[oc], bias' = bias * a + b for a layer that stays dense; returns (W', bias')."""
+    wf = torch.empty_like(weights)
+    bias_out = torch.empty_like(a)
+    M = weights.shape[0]
+    _check(lib.escort_dense_fold_affine(M, C.c_long(weights.numel() // M), _ptr(weights), _ptr(a), _ptr(b), _ptr(bias), _ptr(wf),
+                                        _ptr(bias_out), _stream(stream)), "escort_dense_fold_affine")
+    return wf, bias_out
 
 
 def bn_scale_to_affine(mean, var, scale_factor_blob, eps, gamma=None, beta=None, stream=None):

@@ -858,3 +858,14 @@ extern "C" int escort_plan_fold_affine(escort_plan *p, const float *weights_dens
   p->bwd_tried = tried;
   return rc;
 }
+
+// the same fold for a layer the reference keeps dense (f1): W'[oc][...] = W[oc][...] * a[oc], bias' = bias * a + b
+extern "C" int escort_dense_fold_affine(int num_output, long row, const float *weights, const float *a, const float *b, const float *bias_in,
+                                        float *weights_folded, float *bias_out, escort_stream_t stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  ESCORT_REQUIRE(num_output > 0 && row > 0 && weights && a && weights_folded, "escort_dense_fold_affine: bad arguments");
+  const long total = row * num_output, threads = std::max<long>(total, num_output);
+  fold_affine_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(total, row, num_output, weights, a, b, bias_in, weights_folded, bias_out);
+  ESCORT_LAUNCH_CHECK();
+  return 0;
+}

@@ -222,6 +222,7 @@ struct PwParams {
   int BN, stages, nkb;
   int fuse_relu;
   const float *bias;
+  const float *residual;   // optional second input of an Eltwise SUM behind the convolution (same shape as out; may alias it)
   float *out;
 };
 
@@ -328,17 +329,19 @@ __global__ void __launch_bounds__(kDenseThreads)
     dn_mbar_wait(tmem_full, 0u);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     bool live;
-    float *orow;  // &out[image][n0][pixel]
+    size_t o0;  // index of out[image][n0][pixel]
     if (kImplicit) {
       const int px = p0 + 32 * q + lane;
       live = px < p.HW;
-      orow = p.out + ((size_t)img * p.M + n0) * p.HW + px;
+      o0 = ((size_t)img * p.M + n0) * p.HW + px;
     } else {
       const long row = row0 + 32 * q + lane;
       live = row < p.rows;
       const long im = row / p.HW;
-      orow = p.out + ((size_t)im * p.M + n0) * p.HW + (row - im * p.HW);
+      o0 = ((size_t)im * p.M + n0) * p.HW + (row - im * p.HW);
     }
+    float *orow = p.out + o0;
+    const float *rrow = p.residual ? p.residual + o0 : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < p.BN && n0 + c0 < p.M; c0 += 32) {
       uint32_t v[32];
@@ -353,11 +356,15 @@ __global__ void __launch_bounds__(kDenseThreads)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int mleft = p.M - n0 - c0;
+      float r[32];  // all residual loads of the chunk before its first store: they may alias (in-place Eltwise), and 32
+                    // load -> store pairs in program order would pay 32 dependent global latencies
+#pragma unroll
+      for (int t = 0; t < 32; ++t) r[t] = (rrow && live && t < mleft) ? rrow[(size_t)(c0 + t) * p.HW] : 0.f;
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         float b;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(sbias + 4 * (c0 + t)));
-        float x = __uint_as_float(v[t]) + b;
+        float x = __uint_as_float(v[t]) + b + r[t];
         if (p.fuse_relu) x = fmaxf(x, 0.f);
         if (live && t < mleft) orow[(size_t)(c0 + t) * p.HW] = x;
       }
@@ -456,7 +463,7 @@ bool pointwise_applies(const escort_geom *g, const float *bottom, const float *w
 
 // launch of dense_conv_tf32_kernel: implicit = straight from NCHW (1x1), else from the transposed column buffer
 int launch_conv(bool implicit, const escort_geom *g, int num, int HW, const float *a_src, int K, const float *w_src, const float *bias,
-                int fuse_relu, float *top, cudaStream_t stream) {
+                const float *residual, int fuse_relu, float *top, cudaStream_t stream) {
   const char *what = "escort_dense_conv_forward";
   const int M = g->num_output;
   PwParams prm;
@@ -471,7 +478,7 @@ int launch_conv(bool implicit, const escort_geom *g, int num, int HW, const floa
   prm.ntn = ceil_div(M, prm.BN);
   prm.stages = std::min(prm.nkb, 2);
   if (const char *e = getenv("ESCORT_DENSE_STAGES")) prm.stages = std::max(1, std::min(std::min(prm.nkb, 4), atoi(e)));  // (measurement knob)
-  prm.fuse_relu = fuse_relu, prm.bias = bias, prm.out = top;
+  prm.fuse_relu = fuse_relu, prm.bias = bias, prm.residual = residual, prm.out = top;
   CUtensorMap tx, tw;
   int rc;
   if (implicit) {
@@ -553,9 +560,9 @@ extern "C" ESCORT_API size_t escort_dense_conv_workspace_bytes(const escort_geom
   return ((size_t)num * Ho * Wo + (size_t)g->num_output) * Kp * sizeof(float) + 256;
 }
 
-extern "C" ESCORT_API int escort_dense_conv_forward(const escort_geom *g, int num, const float *bottom, const float *weight, const float *bias,
-                                                    int fuse_relu, void *workspace, size_t workspace_bytes, float *top,
-                                                    escort_stream_t stream_) {
+extern "C" ESCORT_API int escort_dense_conv_forward_residual(const escort_geom *g, int num, const float *bottom, const float *weight,
+                                                             const float *bias, const float *residual, int fuse_relu, void *workspace,
+                                                             size_t workspace_bytes, float *top, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESCORT_REQUIRE(g && num >= 0 && bottom && weight && workspace && top, "escort_dense_conv_forward: null argument");
   ESCORT_REQUIRE(g->group == 1, "escort_dense_conv_forward: group > 1 is not implemented (the reference's dense layers have group 1, AlexNet conv1 included)");
@@ -564,7 +571,7 @@ extern "C" ESCORT_API int escort_dense_conv_forward(const escort_geom *g, int nu
   dense_conv_dims(g, &Ho, &Wo, &K, &Kp);
   if (num == 0 || Ho <= 0 || Wo <= 0) return 0;
   if (pointwise_applies(g, bottom, weight))
-    return launch_conv(true, g, num, Ho * Wo, bottom, g->channels, weight, bias, fuse_relu, top, stream);
+    return launch_conv(true, g, num, Ho * Wo, bottom, g->channels, weight, bias, residual, fuse_relu, top, stream);
   const long rows = (long)num * Ho * Wo;
   ESCORT_REQUIRE(rows < 2147483647L, "escort_dense_conv_forward: batch too large for 32-bit pixel indices");
   float *wpad = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
@@ -576,5 +583,11 @@ extern "C" ESCORT_API int escort_dense_conv_forward(const escort_geom *g, int nu
                                                                          g->kernel_w, g->pad_h, g->pad_w, g->stride_h, g->stride_w,
                                                                          g->dilation_h, g->dilation_w, Ho, Wo, K, Kp, colT);
   ESCORT_LAUNCH_CHECK();
-  return launch_conv(false, g, num, Ho * Wo, colT, Kp, wpad, bias, fuse_relu, top, stream);
+  return launch_conv(false, g, num, Ho * Wo, colT, Kp, wpad, bias, residual, fuse_relu, top, stream);
+}
+
+extern "C" ESCORT_API int escort_dense_conv_forward(const escort_geom *g, int num, const float *bottom, const float *weight, const float *bias,
+                                                    int fuse_relu, void *workspace, size_t workspace_bytes, float *top,
+                                                    escort_stream_t stream_) {
+  return escort_dense_conv_forward_residual(g, num, bottom, weight, bias, nullptr, fuse_relu, workspace, workspace_bytes, top, stream_);
 }

@@ -181,6 +181,12 @@ ESCORT_API size_t escort_dense_conv_workspace_bytes(const escort_geom *geom, int
 ESCORT_API int escort_dense_conv_forward(const escort_geom *geom, int num, const float *bottom, const float *weight,
                                          const float *bias, int fuse_relu, void *workspace, size_t workspace_bytes, float *top,
                                          escort_stream_t stream);
+/* the same convolution with the Eltwise SUM that follows a ResNet branch2c fused into its epilogue
+ * (src/caffe/layers/eltwise_layer.cu, EltwiseParameter_EltwiseOp_SUM with unit coefficients):
+ * top = [relu](conv(bottom) + bias + residual); `residual` has top's shape and may alias top; NULL = plain forward. */
+ESCORT_API int escort_dense_conv_forward_residual(const escort_geom *geom, int num, const float *bottom, const float *weight,
+                                                  const float *bias, const float *residual, int fuse_relu, void *workspace,
+                                                  size_t workspace_bytes, float *top, escort_stream_t stream);
 
 /* ---- f2: glue-layer fusion ------------------------------------------------------------------------------------------
  * conv -> BatchNorm(use_global_stats) -> Scale -> ReLU (the chain around every ResNet-50 sparse conv; the reference runs
@@ -196,6 +202,9 @@ ESCORT_API int escort_bn_scale_to_affine(int num_output, const float *bn_mean, c
                                          escort_stream_t stream);
 ESCORT_API int escort_plan_fold_affine(escort_plan *plan, const float *weights_dense, const float *a, const float *b,
                                        const float *bias_in, float *weights_folded, float *bias_out, escort_stream_t stream);
+/* the same fold for a layer that stays dense (f1): weights [num_output x row] -> weights_folded (may alias), bias_out = bias_in * a + b */
+ESCORT_API int escort_dense_fold_affine(int num_output, long row, const float *weights, const float *a, const float *b,
+                                        const float *bias_in, float *weights_folded, float *bias_out, escort_stream_t stream);
 
 /* ---- f3: the LOWERED_SPARSE comparator -----------------------------------------------------------------------------
  * conv_mode 1 of the reference: per image im2col, then per group CSR x dense on cuSPARSE

@@ -167,7 +167,7 @@ class Plan:
     def kernel_names(self):
         """{'fwd': ..., 'bwd_data': ..., 'bwd_weight': ...}: kernels in use (backward entries once those plans exist)."""
         parts = self.describe().split(" | ")
-        out = {"fwd": parts[0].split(" ")[0] if parts[0] != "generic" else "sconv_fwd_generic",
+        out = {"fwd": parts[0].split(" ")[0] if parts[0] != "generic" else self.kernel_name,   # sconv_fwd_generic / sconv_fwd_small
                "bwd_data": "sconv_bwd_data_generic", "bwd_weight": "sconv_bwd_weight_generic"}
         for p in parts[1:]:
             k, v = p.split(": ", 1)

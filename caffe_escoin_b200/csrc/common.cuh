@@ -86,6 +86,7 @@ struct escort_plan {
   int tile_w_tried;
   // ---- knobs read ONCE at plan creation (never getenv on the launch path) and the lock of the lazy builds
   int generic_backward;   // ESCORT_GENERIC_BACKWARD: keep the backward on the generic kernels (tests)
+  int small_maps;         // 0 with ESCORT_NO_SMALL_MAPS: variant 0 is always the generic kernel, never the small-map one (tests)
   std::mutex *mu;         // guards the first-use builds of bwd / tile_w when several host threads share a plan
 };
 

@@ -119,6 +119,74 @@ __global__ void __launch_bounds__(kGenThreads)
 }
 
 // ------------------------------------------------------------------------------------------------------
+// small maps (LeNet-sized layers, where a persistent tile kernel has fewer units than the GPU has SMs and the
+// generic kernel's blocks are a fraction of a warp's worth of pixels): one CTA = one image x a slice of the output
+// channels, the WHOLE input image staged once in shared memory; a warp takes (output channel, 64 pixels) items, two
+// pixels per lane, and walks the channel's CSR row with warp-uniform 16-byte loads of the same meta records the generic
+// kernel uses.  Same accumulation order as the generic kernel (bias first, then CSR order): bit-identical results.
+// ------------------------------------------------------------------------------------------------------
+static constexpr int kSmallThreads = 256;
+static constexpr size_t kSmallMaxBytes = 96 * 1024;
+
+template <bool kHalo>  // false: no padding, every tap of every output is inside the image -- no bounds tests in the loop
+__global__ void __launch_bounds__(kSmallThreads)
+    sconv_fwd_small_kernel(const int *__restrict__ rowptr, const int4 *__restrict__ meta, const float *__restrict__ bottom,
+                           const float *__restrict__ bias, int fuse_relu, float *__restrict__ top, int CHW, int H, int W, int M,
+                           int Ho, int Wo, int stride_h, int stride_w, int splits, int oc_per_cta) {
+  extern __shared__ __align__(16) float img_s[];
+  const int n = blockIdx.x / splits, part = blockIdx.x - n * splits;
+  const float *src = bottom + (size_t)n * CHW;
+  if ((CHW & 3) == 0 && ((uintptr_t)src & 15) == 0) {
+    for (int i = threadIdx.x; i < (CHW >> 2); i += kSmallThreads) reinterpret_cast<float4 *>(img_s)[i] = __ldg(reinterpret_cast<const float4 *>(src) + i);
+  } else {
+    for (int i = threadIdx.x; i < CHW; i += kSmallThreads) img_s[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int HoWo = Ho * Wo, pblocks = (HoWo + 63) / 64;
+  const int oc0 = part * oc_per_cta, oc1 = min(M, oc0 + oc_per_cta);
+  const int items = (oc1 - oc0) * pblocks;
+  // the warp's window of 32 records: loaded with one coalesced 512-byte access (a record is read by one warp once, so a
+  // per-record uniform load would pay an L2 latency per nonzero), read back as broadcasts
+  int4 *mw = reinterpret_cast<int4 *>(img_s + ((CHW + 3) & ~3)) + wid * 32;
+  for (int it = wid; it < items; it += kSmallThreads / 32) {
+    const int oc = oc0 + it / pblocks, pb = it - (it / pblocks) * pblocks;
+    const int pa = pb * 64 + lane, pc = pa + 32;
+    const bool la = pa < HoWo, lc = pc < HoWo;
+    const int oya = la ? pa / Wo : 0, oxa = la ? pa - oya * Wo : 0;
+    const int oyc = lc ? pc / Wo : 0, oxc = lc ? pc - oyc * Wo : 0;
+    const int iya = oya * stride_h, ixa = oxa * stride_w, iyc = oyc * stride_h, ixc = oxc * stride_w;
+    const int ba = iya * W + ixa, bc = iyc * W + ixc;
+    float sa = bias ? __ldg(bias + oc) : 0.f, sc = sa;
+    const int j1 = __ldg(rowptr + oc + 1);
+    int j0 = __ldg(rowptr + oc);
+    int4 nxt = make_int4(0, 0, 0, 0);
+    if (j0 + lane < j1) nxt = __ldg(meta + j0 + lane);
+    for (; j0 < j1; j0 += 32) {
+      __syncwarp();
+      mw[lane] = nxt;
+      __syncwarp();
+      if (j0 + 32 + lane < j1) nxt = __ldg(meta + j0 + 32 + lane);  // the next window is in flight during this one
+      const int len = min(32, j1 - j0);
+#pragma unroll 4
+      for (int i = 0; i < len; ++i) {
+        const int4 m = mw[i];
+        const float w = __int_as_float(m.w);
+        if (!kHalo || ((unsigned)(iya + m.y) < (unsigned)H && (unsigned)(ixa + m.z) < (unsigned)W)) sa = fmaf(w, img_s[ba + m.x], sa);
+        if (!kHalo || ((unsigned)(iyc + m.y) < (unsigned)H && (unsigned)(ixc + m.z) < (unsigned)W)) sc = fmaf(w, img_s[bc + m.x], sc);
+      }
+    }
+    if (fuse_relu) {
+      sa = fmaxf(sa, 0.f);
+      sc = fmaxf(sc, 0.f);
+    }
+    float *out = top + ((size_t)n * M + oc) * HoWo;
+    if (la) out[pa] = sa;
+    if (lc) out[pc] = sc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // generic backward-data: bottom_diff[n][c][iy][ix] = sum over nonzeros (oc,c,kh,kw) of
 //   w * top_diff[n][oc][(iy - dy)/sh][(ix - dx)/sw]   when divisible and in range.  Overwrites.
 // tmeta (grouped by input channel c) = {oc, dy, dx, value}.
@@ -382,6 +450,7 @@ extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, co
   p->layout_rank = 0;
   p->host_nz = nzs;
   p->generic_backward = getenv("ESCORT_GENERIC_BACKWARD") ? 1 : 0;
+  p->small_maps = getenv("ESCORT_NO_SMALL_MAPS") ? 0 : 1;
   p->mu = new std::mutex();
   cudaGetDevice(&p->device);
 
@@ -515,7 +584,8 @@ extern "C" const char *escort_plan_kernel_name(const escort_plan *p) {
   if (!p) return "null";
   if (p->tm) return tmem_kernel_name(p->tm);
   if (p->tile) return tile_kernel_name(p->tile);
-  return "sconv_fwd_generic";
+  const size_t img_bytes = (size_t)p->g.channels * p->g.height * p->g.width * sizeof(float);
+  return (img_bytes <= kSmallMaxBytes && p->small_maps) ? "sconv_fwd_small" : "sconv_fwd_generic";
 }
 
 extern "C" int escort_plan_set_variant(escort_plan *p, int variant) {
@@ -693,6 +763,25 @@ extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom
   }
   ESCORT_REQUIRE(p->d_rowptr, "escort_sconv_forward: this launch needs the generic kernel, which a backward sub-plan does not have");
   const escort_geom &g = p->g;
+  const size_t img_bytes = (size_t)g.channels * g.height * g.width * sizeof(float);
+  if (img_bytes <= kSmallMaxBytes && p->small_maps) {  // the whole input image fits in shared memory: the small-map kernel
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(sconv_fwd_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallMaxBytes + 4096 + 16);
+      cudaFuncSetAttribute(sconv_fwd_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmallMaxBytes + 4096 + 16);
+    });
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, p->device);
+    const int splits = std::max(1, std::min(g.num_output, ceil_div(2 * sms, num)));
+    const int oc_per_cta = ceil_div(g.num_output, splits);
+    const size_t smem = ((img_bytes + 15) & ~(size_t)15) + kSmallThreads / 32 * 32 * sizeof(int4);
+    auto kern = (g.pad_h == 0 && g.pad_w == 0) ? sconv_fwd_small_kernel<false> : sconv_fwd_small_kernel<true>;
+    kern<<<(unsigned)(num * splits), kSmallThreads, smem, stream>>>(p->d_rowptr, p->d_meta, bottom, bias, fuse_relu, top,
+                                                                  g.channels * g.height * g.width, g.height, g.width, g.num_output, p->Ho,
+                                                                  p->Wo, g.stride_h, g.stride_w, splits, oc_per_cta);
+    ESCORT_LAUNCH_CHECK();
+    return 0;
+  }
   dim3 grid(ceil_div(p->Ho * p->Wo, kGenThreads), g.num_output, num);
   ESCORT_REQUIRE(num <= 65535, "escort_sconv_forward: batch too large for the generic kernel");
   sconv_fwd_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_rowptr, p->d_meta, bottom, bias, fuse_relu, top,

@@ -162,6 +162,38 @@ def test_forward_vs_oracle(capi, po, case):
         assert po.rel_l2(y, y_dense) < TOL, name
 
 
+@pytest.mark.parametrize("case", FWD_CASES, ids=lambda c: "N%d_C%d_M%d_H%dx%d_k%dx%d_s%d_p%d_d%d_g%d_sp%g" % c[:12])
+def test_small_map_kernel_is_bit_identical_to_the_generic_kernel(capi, po, case, monkeypatch):
+    """Variant 0 runs sconv_fwd_small where the input image fits in shared memory (LeNet-sized layers) and
+    sconv_fwd_generic otherwise (or with ESCORT_NO_SMALL_MAPS, read at plan creation): same records, same accumulation
+    order -- the two must agree bit for bit, and both with the oracle."""
+    from caffe_escoin_b200 import workloads as wl
+    torch = _torch()
+    N, Cin, Cout, H, W, kh, kw, s, p, dil, grp, sp, has_bias, relu = case
+    rng = np.random.default_rng(hash(case[:12]) % (2 ** 31))
+    w = (rng.standard_normal((Cout, Cin // grp, kh, kw)) * 0.01).astype(np.float32)
+    w = wl.prune_magnitude(w, sp) if sp < 1.0 else np.zeros_like(w)
+    bias = (rng.standard_normal(Cout) * 0.1).astype(np.float32) if has_bias else None
+    x = rng.uniform(-1, 1, (N, Cin, H, W)).astype(np.float32)
+    g = po.Geom(N, Cin, H, W, Cout, kh, s, p, dil, grp, kw=kw)
+    y_or = po.conv_forward(x, po.weight_align(w, g), g, bias, relu=relu)
+    geom = capi.make_geom(Cin, Cout, H, W, kh, s, p, dil, grp, kw=kw)
+    wd = torch.from_numpy(w).cuda()
+    xd = torch.from_numpy(x).cuda()
+    bd = torch.from_numpy(bias).cuda() if has_bias else None
+    outs = {}
+    for no_small in (False, True):
+        if no_small:
+            monkeypatch.setenv("ESCORT_NO_SMALL_MAPS", "1")
+        plan = capi.Plan(geom, capi.weight_align(wd, geom))
+        plan.set_variant(0)
+        fits = Cin * H * W * 4 <= 96 * 1024   # (the 8 x 56 x 56 case is 2 KB over: generic both times)
+        assert plan.kernel_name == ("sconv_fwd_small" if fits and not no_small else "sconv_fwd_generic")
+        outs[no_small] = plan.forward(xd, bd, relu=relu).cpu().numpy()
+    assert np.array_equal(outs[False], outs[True])
+    assert po.rel_l2(outs[False], y_or) < TOL
+
+
 def test_forward_raw_and_stretched_plans_agree(capi, po):
     from caffe_escoin_b200 import workloads as wl
     spec = wl.ALEXNET[3]._replace(N=2, Cin=32, Cout=32)

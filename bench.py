@@ -62,21 +62,78 @@ def _workload(name, train=False):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe).  NVML -- the library behind
+    nvidia-smi -- polled every 5 ms from a thread, so that a region of a few milliseconds still gets samples (an
+    `nvidia-smi -lms` child needs ~100 ms to start and misses an 18 ms region); the nvidia-smi child remains the fallback
+    where pynvml is missing.  stop() always returns at least one sample (taken right after the region if none fell in)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.proc = None
+        self.thread = None
+        self.samples = []     # (sm_mhz, max_mhz, reason bitmask)
+        self._stop = False
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._sample()
+            self.samples.clear()
+            import threading
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                              "--format=csv,noheader,nounits", "-lms", "100"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
+
+    def _sample(self):
+        nv = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        try:
+            mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+            mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        self.samples.append((float(sm), float(mx), int(mask)))
+
+    def _run(self):
+        while not self._stop:
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.005)
+
+    def _summary(self, sm, mx, reasons, n, note=None):
+        busy = sorted(sm)[len(sm) // 2:]   # samples under load = the upper half (the sampler also sees the idle edges)
+        out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": n}
+        if note:
+            out["note"] = note
+        return out
 
     def stop(self):
+        if self.thread is not None:
+            self._stop = True
+            self.thread.join(timeout=2)
+            note = None
+            if not self.samples:
+                try:
+                    self._sample()
+                    note = "no sample fell inside the region: one taken right after it"
+                except Exception:
+                    return None
+            reasons = {n for n, bit in self.REASONS for s_ in self.samples if s_[2] & bit}
+            return self._summary([s_[0] for s_ in self.samples], [s_[1] for s_ in self.samples], reasons,
+                                 0 if note else len(self.samples), note)
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -102,10 +159,7 @@ class ClockSampler:
                     reasons.add(n)
         if not sm:
             return None
-        # samples under load = the upper half (the sampler also sees the idle edges of the region)
-        busy = sorted(sm)[len(sm) // 2:]
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return self._summary(sm, mx, reasons, len(sm))
 
 
 # ----------------------------------------------------------------------------------------------------------------

@@ -28,7 +28,7 @@
 namespace escort {
 namespace {
 
-constexpr int kBM = 128, kBN = 128, kBK = 32;  // tile: rows of A, rows of B, floats of K per stage (128 bytes = one swizzle row)
+constexpr int kBM = 128, kBN = 128, kBK = 32;  // tile: rows of A, most rows of B, floats of K per stage (128 bytes = one swizzle row)
 constexpr int kStages = 6;
 constexpr int kStageBytes = (kBM + kBN) * kBK * 4;  // 32 KiB
 constexpr int kDenseThreads = 192;                  // warp 0: TMA, warp 1: MMA + TMEM alloc, warps 2-5: epilogue
@@ -86,6 +86,7 @@ __device__ __forceinline__ uint64_t dn_smem_desc(unsigned saddr) {
 struct DenseParams {
   int rows_a, rows_b, K;     // D is rows_a x rows_b: out[i * ldo + j], bias[j]
   int ldo;
+  int BN;                    // rows of B per tile: 128, or 64 when 128 would leave SMs without a tile
   int fuse_relu;
   const float *bias;
   float *out;
@@ -100,7 +101,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
   const unsigned full0 = bars, empty0 = bars + 8 * kStages, tmem_full = bars + 16 * kStages, tslot = tmem_full + 8;
   const int tid = threadIdx.x, lane = tid & 31;
   const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * kBN;
+  const int m0 = blockIdx.x * kBM, n0 = blockIdx.y * p.BN;
+  const int stage_bytes = (kBM + p.BN) * kBK * 4;
   const int nkb = (p.K + kBK - 1) / kBK;
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -125,8 +127,8 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         dn_mbar_wait(empty0 + 8 * s, (unsigned)(((kb / kStages) & 1) ^ 1));  // a fresh barrier passes the first round
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * s), "r"((unsigned)kStageBytes) : "memory");
-        const unsigned sa = base + s * kStageBytes, sb = sa + kBM * kBK * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full0 + 8 * s), "r"((unsigned)stage_bytes) : "memory");
+        const unsigned sa = base + s * stage_bytes, sb = sa + kBM * kBK * 4;
         asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(sa),
                      "l"(&tmap_a), "r"(kb * kBK), "r"(m0), "r"(full0 + 8 * s)
                      : "memory");
@@ -139,12 +141,12 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
     if (lane == 0) {  // ---- MMA issuer ----
       // instruction descriptor (kind::tf32): D = F32 (bits 4-5 = 1), A = B = TF32 (bits 7-9, 10-12 = 2), both K-major,
       // N >> 3 at bits 17-22, M >> 4 at bits 24-28
-      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(kBN >> 3) << 17) | ((unsigned)(kBM >> 4) << 24);
+      const unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(p.BN >> 3) << 17) | ((unsigned)(kBM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % kStages;
         dn_mbar_wait(full0 + 8 * s, (unsigned)((kb / kStages) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const unsigned sa = base + s * kStageBytes, sb = sa + kBM * kBK * 4;
+        const unsigned sa = base + s * stage_bytes, sb = sa + kBM * kBK * 4;
         const uint64_t da = dn_smem_desc(sa), db = dn_smem_desc(sb);
 #pragma unroll
         for (int k = 0; k < kBK / 8; ++k) {
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(kDenseThreads, 1)
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int i = m0 + 32 * q + lane;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kBN; c0 += 32) {
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
       uint32_t v[32];
       const uint32_t taddr = tbase + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
       asm volatile(
@@ -236,7 +238,7 @@ __device__ __forceinline__ uint64_t pw_desc_a(unsigned saddr) {  // MN-major, SW
   return d;
 }
 
-template <bool kImplicit>
+template <bool kImplicit, bool kResidual>  // kResidual keeps 32 more registers live in the epilogue: its own instantiation
 __global__ void __launch_bounds__(kDenseThreads)
     dense_conv_tf32_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w, const PwParams p) {
   extern __shared__ unsigned char dsm_raw[];
@@ -341,7 +343,7 @@ __global__ void __launch_bounds__(kDenseThreads)
       o0 = ((size_t)im * p.M + n0) * p.HW + (row - im * p.HW);
     }
     float *orow = p.out + o0;
-    const float *rrow = p.residual ? p.residual + o0 : nullptr;
+    [[maybe_unused]] const float *rrow = kResidual ? p.residual + o0 : nullptr;
 #pragma unroll 1
     for (int c0 = 0; c0 < p.BN && n0 + c0 < p.M; c0 += 32) {
       uint32_t v[32];
@@ -356,15 +358,19 @@ __global__ void __launch_bounds__(kDenseThreads)
           : "memory");
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       const int mleft = p.M - n0 - c0;
-      float r[32];  // all residual loads of the chunk before its first store: they may alias (in-place Eltwise), and 32
-                    // load -> store pairs in program order would pay 32 dependent global latencies
+      [[maybe_unused]] float r[kResidual ? 32 : 1];  // all residual loads of the chunk before its first store: they may alias
+                                                     // (in-place Eltwise), and 32 load -> store pairs in program order would
+                                                     // pay 32 dependent global latencies
+      if constexpr (kResidual) {
 #pragma unroll
-      for (int t = 0; t < 32; ++t) r[t] = (rrow && live && t < mleft) ? rrow[(size_t)(c0 + t) * p.HW] : 0.f;
+        for (int t = 0; t < 32; ++t) r[t] = (live && t < mleft) ? rrow[(size_t)(c0 + t) * p.HW] : 0.f;
+      }
 #pragma unroll
       for (int t = 0; t < 32; ++t) {
         float b;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(sbias + 4 * (c0 + t)));
-        float x = __uint_as_float(v[t]) + b + r[t];
+        float x = __uint_as_float(v[t]) + b;
+        if constexpr (kResidual) x += r[t];
         if (p.fuse_relu) x = fmaxf(x, 0.f);
         if (live && t < mleft) orow[(size_t)(c0 + t) * p.HW] = x;
       }
@@ -418,7 +424,7 @@ __global__ void pad_rows_kernel(long total, const float *__restrict__ src, int K
   dst[e] = k < K ? __ldg(src + (e / Kp) * K + k) : 0.f;
 }
 
-int encode_2d(CUtensorMap *out, const float *ptr, int rows, int K, const char *what) {
+int encode_2d(CUtensorMap *out, const float *ptr, int rows, int K, int box_rows, const char *what) {
   TmaEncodeFn enc = dense_tma_encoder();
   if (!enc) {
     set_last_error(std::string(what) + ": cuTensorMapEncodeTiled is not available");
@@ -426,7 +432,7 @@ int encode_2d(CUtensorMap *out, const float *ptr, int rows, int K, const char *w
   }
   const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)K * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBM};
+  const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -500,30 +506,40 @@ int launch_conv(bool implicit, const escort_geom *g, int num, int HW, const floa
     if ((rc = encode_tiled(&tw, w_src, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, what))) return rc;
   }
   const int smem = prm.stages * (kPwABytes + prm.BN * kBK * 4) + 1024 /* alignment slack */ + 128 /* barriers */ + 1024 /* bias */;
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const PwParams);
+  static const Kern kerns[4] = {dense_conv_tf32_kernel<false, false>, dense_conv_tf32_kernel<false, true>, dense_conv_tf32_kernel<true, false>,
+                                dense_conv_tf32_kernel<true, true>};
   static std::once_flag once;
   std::call_once(once, [] {
     const int most = 4 * (kPwABytes + 256 * kBK * 4) + 2176;
-    cudaFuncSetAttribute(dense_conv_tf32_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
-    cudaFuncSetAttribute(dense_conv_tf32_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+    for (Kern k : kerns) {
+      cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, most);
+      // (the driver's default carve-out keeps 3 CTAs of the 48 KB shape per SM; forcing the maximum carve-out for a 4th
+      // was measured 5-10 % slower on every layer)
+    }
   });
   const long tiles = implicit ? (long)num * prm.tiles_per_img : (prm.rows + kPwBM - 1) / kPwBM;
   const long ctas = tiles * prm.ntn;
   ESCORT_REQUIRE(ctas < 2147483647L, "escort_dense_conv_forward: batch too large for one launch");
-  if (implicit)
-    dense_conv_tf32_kernel<true><<<(unsigned)ctas, kDenseThreads, smem, stream>>>(tx, tw, prm);
-  else
-    dense_conv_tf32_kernel<false><<<(unsigned)ctas, kDenseThreads, smem, stream>>>(tx, tw, prm);
+  kerns[(implicit ? 2 : 0) + (residual ? 1 : 0)]<<<(unsigned)ctas, kDenseThreads, smem, stream>>>(tx, tw, prm);
   ESCORT_LAUNCH_CHECK();
   return 0;
 }
 
-int launch_gemm(const float *A, int rows_a, const float *B, int rows_b, int K, const DenseParams &prm, cudaStream_t stream, const char *what) {
+int launch_gemm(const float *A, int rows_a, const float *B, int rows_b, int K, DenseParams prm, cudaStream_t stream, const char *what) {
+  // 128 x 128 tiles unless they would leave SMs idle: a small-batch inner product streams its weights once, and one SM
+  // cannot pull more than its share of the HBM bandwidth (fc6 at batch 256: 64 tiles on 148 SMs)
+  int sms = 148, dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  prm.BN = (ceil_div(rows_a, kBM) * ceil_div(rows_b, kBN) < sms && rows_b > 64) ? 64 : kBN;
+  if (const char *e = getenv("ESCORT_DENSE_FC_BN")) prm.BN = atoi(e) == 64 ? 64 : kBN;  // (measurement knob)
   CUtensorMap ta, tb;
   int rc;
-  if ((rc = encode_2d(&ta, A, rows_a, K, what)) || (rc = encode_2d(&tb, B, rows_b, K, what))) return rc;
+  if ((rc = encode_2d(&ta, A, rows_a, K, kBM, what)) || (rc = encode_2d(&tb, B, rows_b, K, prm.BN, what))) return rc;
   static std::once_flag once;
   std::call_once(once, [] { cudaFuncSetAttribute(dense_gemm_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDenseSmem); });
-  const dim3 grid((unsigned)ceil_div(rows_a, kBM), (unsigned)ceil_div(rows_b, kBN));
+  const dim3 grid((unsigned)ceil_div(rows_a, kBM), (unsigned)ceil_div(rows_b, prm.BN));
   dense_gemm_tf32_kernel<<<grid, kDenseThreads, kDenseSmem, stream>>>(ta, tb, prm);
   ESCORT_LAUNCH_CHECK();
   return 0;
@@ -541,7 +557,7 @@ extern "C" ESCORT_API int escort_inner_product_forward(int num, int K, int num_o
   ESCORT_REQUIRE(K % 4 == 0 && ((uintptr_t)bottom & 15) == 0 && ((uintptr_t)weight & 15) == 0,
                  "escort_inner_product_forward: K must be a multiple of 4 and the operands 16-byte aligned (TMA row pitch)");
   if (num == 0) return 0;
-  DenseParams prm = {num, num_output, K, num_output, fuse_relu, bias, top};
+  DenseParams prm = {num, num_output, K, num_output, kBN, fuse_relu, bias, top};
   return launch_gemm(bottom, num, weight, num_output, K, prm, stream, "escort_inner_product_forward");
 }
 

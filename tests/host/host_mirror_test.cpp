@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../caffe_escoin_b200/host/escort_conv_layer.hpp"
+#include "../../caffe_escoin_b200/host/escort_dense_layers.hpp"
 
 extern "C" {
 void oracle_dense_conv(const float *bottom, int num, int Cin, int H, int W, const float *weights, int Cout, int group,
@@ -184,6 +185,71 @@ static void error_behaviour() {
   printf("[ %s ] ErrorBehaviour\n", g_fail == fails_before ? "      OK" : " FAILED ");
 }
 
+// ---- the layers the reference keeps dense (f1), TF32 on tcgen05: EXPECT_NEAR at the TF32 bar (2e-3 relative L2) ----
+static void inner_product_forward(int num, int c, int h, int w, int num_output, bool bias) {  // test_inner_product_layer.cpp TestForward
+  printf("[ RUN      ] InnerProductForward_%dx%dx%dx%d_to_%d\n", num, c, h, w, num_output);
+  const int fails_before = g_fail;
+  std::mt19937 rng(1701);
+  std::uniform_real_distribution<float> uni(-1.f, 1.f);
+  InnerProductParameter ip;
+  ip.num_output = num_output;
+  ip.bias_term = bias;
+  InnerProductLayer layer(ip);
+  Blob bottom, top;
+  bottom.Reshape({num, c, h, w});
+  layer.LayerSetUp(bottom.shape);
+  top.Reshape(layer.top_shape());
+  const int K = c * h * w;
+  std::vector<float> wv(layer.blobs()[0].count()), b(bias ? num_output : 0), x(bottom.count());
+  for (float &v : wv) v = uni(rng) / std::sqrt((float)K);
+  for (float &v : b) v = uni(rng);
+  for (float &v : x) v = uni(rng);
+  h2d(layer.blobs()[0].mutable_gpu_data(), wv);
+  if (bias) h2d(layer.blobs()[1].mutable_gpu_data(), b);
+  h2d(bottom.mutable_gpu_data(), x);
+  layer.Forward_gpu(bottom, top);
+  cuda_check(cudaDeviceSynchronize(), "inner product forward");
+  std::vector<float> ref(top.count());
+  // an inner product is a 1x1 convolution of a K-channel 1x1 image
+  oracle_dense_conv(x.data(), num, K, 1, 1, wv.data(), num_output, 1, 1, 1, 0, 0, 1, 1, 1, 1, bias ? b.data() : nullptr, 0, ref.data());
+  std::vector<float> got = d2h(top.gpu_data(), top.count());
+  EXPECT(rel_l2(got, ref) < 2e-3, "inner product: rel_l2 %.3g", rel_l2(got, ref));
+  printf("[ %s ] InnerProductForward\n", g_fail == fails_before ? "      OK" : " FAILED ");
+}
+
+static void esc_convolution_forward(const char *name, int num, int channels, int hw, const ConvolutionParameter &p, bool residual) {
+  printf("[ RUN      ] EscConvolution_%s\n", name);
+  const int fails_before = g_fail;
+  std::mt19937 rng(1701);
+  std::uniform_real_distribution<float> uni(-1.f, 1.f);
+  EscConvolutionLayer layer(p, /*fuse_relu=*/residual);
+  Blob bottom, top, shortcut;
+  bottom.Reshape({num, channels, hw, hw});
+  layer.LayerSetUp(bottom.shape);
+  top.Reshape(layer.top_shape());
+  shortcut.Reshape(layer.top_shape());
+  std::vector<float> wv(layer.blobs()[0].count()), b(p.bias_term ? p.num_output : 0), x(bottom.count()), r(top.count());
+  const float scale = 1.f / std::sqrt((float)(channels * p.kernel_h * p.kernel_w));
+  for (float &v : wv) v = uni(rng) * scale;
+  for (float &v : b) v = uni(rng);
+  for (float &v : x) v = uni(rng);
+  for (float &v : r) v = uni(rng);
+  h2d(layer.blobs()[0].mutable_gpu_data(), wv);
+  if (p.bias_term) h2d(layer.blobs()[1].mutable_gpu_data(), b);
+  h2d(bottom.mutable_gpu_data(), x);
+  h2d(shortcut.mutable_gpu_data(), r);
+  layer.Forward_gpu(bottom, top, residual ? &shortcut : nullptr);
+  cuda_check(cudaDeviceSynchronize(), "dense conv forward");
+  std::vector<float> ref(top.count());
+  oracle_dense_conv(x.data(), num, channels, hw, hw, wv.data(), p.num_output, 1, p.kernel_h, p.kernel_w, p.pad_h, p.pad_w, p.stride_h,
+                    p.stride_w, p.dilation_h, p.dilation_w, p.bias_term ? b.data() : nullptr, 0, ref.data());
+  if (residual)
+    for (size_t i = 0; i < ref.size(); ++i) ref[i] = std::max(ref[i] + r[i], 0.f);  // Eltwise SUM + ReLU
+  std::vector<float> got = d2h(top.gpu_data(), top.count());
+  EXPECT(rel_l2(got, ref) < 2e-3, "dense convolution: rel_l2 %.3g", rel_l2(got, ref));
+  printf("[ %s ] EscConvolution_%s\n", g_fail == fails_before ? "      OK" : " FAILED ", name);
+}
+
 int main() {
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -211,6 +277,11 @@ int main() {
   for (const Case &c : cases) run_case(c);
   sobel_known_answer();
   error_behaviour();
+  inner_product_forward(2, 3, 4, 5, 10, true);      // test_inner_product_layer.cpp: bottom 2x3x4x5, num_output 10 (K = 60)
+  inner_product_forward(130, 9, 2, 2, 257, false);  // ragged in every dimension of the 128-row tiles
+  esc_convolution_forward("Conv1Like_k7_s2_p3", 2, 3, 30, P(16, 7, 2, 3, 1, true), false);
+  esc_convolution_forward("Pointwise_implicit_gemm", 3, 36, 14, P(72, 1, 1, 0, 1, true), false);
+  esc_convolution_forward("Branch2c_residual_relu", 2, 32, 12, P(96, 1, 1, 0, 1, true), true);
   printf(g_fail ? "[  FAILED  ] %d expectation(s)\n" : "[  PASSED  ] all host-mirror tests\n", g_fail);
   return g_fail ? 1 : 0;
 }

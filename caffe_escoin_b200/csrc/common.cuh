@@ -81,6 +81,12 @@ struct escort_plan {
   // 180-degree rotated weights (stride 1 only).  Built on first use; owns only g / nnz / host_nz / d_dense_idx / tile.
   escort_plan *bwd;
   int bwd_tried;
+  // ---- stride-2 forward as a stride-1 convolution over the space-to-depth of the padded input (core.cu build_s2d_plan):
+  // a forward sub-plan over 4 x channels parity planes with a ceil(K / 2) kernel, and the library-owned transformed input
+  escort_plan *s2d;
+  int use_s2d;          // the forward goes through s2d (default when the sub-plan exists; escort_plan_autotune measures both)
+  float *s2d_buf;       // [num][4 * channels][Ho + KH2 - 1][Wo + KW2 - 1], grown on demand
+  size_t s2d_elems;
   // ---- backward weight through the tile kernel's "W" variants (stride 1 only), built on first use
   escort::TilePlan *tile_w;
   int tile_w_tried;

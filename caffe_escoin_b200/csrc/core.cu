@@ -359,6 +359,8 @@ extern "C" int escort_sconv_padded(int fuse_relu, int num, const float *input, i
   return 0;
 }
 
+static int build_s2d_plan(escort_plan *p, cudaStream_t stream);
+
 extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, const int *colidx, const float *values,
                                   int colidx_is_stretched, escort_plan **plan_out, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -486,6 +488,7 @@ extern "C" int escort_plan_create(const escort_geom *geom, const int *rowptr, co
     return rc;
   }
   rc = tile_plan_build(p, -1, stream);
+  if (!rc) rc = build_s2d_plan(p, stream);  // stride 2: the space-to-depth sub-plan (stride-1 kernels), default path when it exists
   if (rc) {
     escort_plan_destroy(p);
     return rc;
@@ -509,6 +512,8 @@ extern "C" int escort_plan_destroy(escort_plan *p) {
   if (p->tm) tmem_plan_free(p->tm);
   if (p->tile_w) tile_plan_free(p->tile_w);
   if (p->bwd) escort_plan_destroy(p->bwd);
+  if (p->s2d) escort_plan_destroy(p->s2d);
+  cudaFree(p->s2d_buf);
   delete p->host_nz;
   delete p->mu;
   delete p;
@@ -567,8 +572,10 @@ static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
     return rc;
   }
   q->parent = p;
-  if (p->refreshed && p->d_meta) {
-    rc = tile_regather(q, p->d_meta, stream);
+  const escort_plan *root = p;
+  while (root->parent) root = root->parent;  // (p may itself be the space-to-depth sub-plan of a stride-2 layer)
+  if (root->refreshed && root->d_meta) {
+    rc = tile_regather(q, root->d_meta, stream);
     if (rc) {
       escort_plan_destroy(q);
       return rc;
@@ -578,10 +585,110 @@ static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
   return 0;
 }
 
+// Stride-2 forward without a stride-2 kernel.  With P = the zero-padded input,
+//   out[oy][ox] = sum w[kh][kw] * P[2 oy + kh][2 ox + kw] = sum w[kh][kw] * P_{kh & 1, kw & 1}[oy + (kh >> 1)][ox + (kw >> 1)]
+// where P_{py,px}[y][x] = P[2 y + py][2 x + px] are the four parity planes of P: a stride-2 K x K convolution with padding
+// is a VALID stride-1 convolution with a ceil(K / 2) kernel over 4 x channels planes of (Ho + KH2 - 1) x (Wo + KW2 - 1)
+// (space-to-depth).  The nonzeros map one to one, (ic, kh, kw) -> (4 ic + 2 (kh & 1) + (kw & 1), kh >> 1, kw >> 1), so
+// the sub-plan is a forward plan over the same weights (same refresh path as the backward-data sub-plan) and runs on
+// the stride-1 TMEM / tile kernels; the parity planes are written by one extra pass over the input (s2d_pad_kernel).
+__global__ void s2d_pad_kernel(long total, const float *__restrict__ in, int C, int H, int W, int pad_h, int pad_w, int H2, int W2,
+                               float *__restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int x2 = (int)(e % W2);
+  long r = e / W2;
+  const int y2 = (int)(r % H2);
+  r /= H2;
+  const int vc = (int)(r % (4 * C));
+  const long n = r / (4 * C);
+  const int ic = vc >> 2, py = (vc >> 1) & 1, px = vc & 1;
+  const int y = 2 * y2 + py - pad_h, x = 2 * x2 + px - pad_w;
+  float v = 0.f;
+  if ((unsigned)y < (unsigned)H && (unsigned)x < (unsigned)W) v = __ldg(in + ((n * C + ic) * H + y) * W + x);
+  out[e] = v;
+}
+
+// Without a measurement (no escort_plan_autotune): the parity-plane path wins on the larger layers of the stride-2 sweep
+// (channels x height >= 128 x 56: 1.1-1.5x, profiles/r02_sweep_config5_stride2.txt) and loses on the small ones, where
+// a window of the 4 x channels planes meets about one tap per output channel.
+// the inverse map for the backward data: bottom_diff[n][c][y][x] = dP_{py,px}[y2][x2] with 2 y2 + py = y + pad (a pixel
+// beyond the last window of the layer belongs to no parity-plane element: its gradient is zero)
+__global__ void d2s_unpad_kernel(long total, const float *__restrict__ dplanes, int C, int H, int W, int pad_h, int pad_w, int H2, int W2,
+                                 float *__restrict__ out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const int x = (int)(e % W);
+  long r = e / W;
+  const int y = (int)(r % H);
+  r /= H;
+  const int c = (int)(r % C);
+  const long n = r / C;
+  const int yp = y + pad_h, xp = x + pad_w;
+  const int y2 = yp >> 1, x2 = xp >> 1, vc = 4 * c + 2 * (yp & 1) + (xp & 1);
+  out[e] = (y2 < H2 && x2 < W2) ? __ldg(dplanes + ((n * 4 * C + vc) * H2 + y2) * W2 + x2) : 0.f;
+}
+
+static int s2d_by_default(const escort_plan *p) {
+  return p->s2d && (long)(p->g.channels / p->g.group) * p->g.height >= 128L * 56 ? 1 : 0;
+}
+
+static int build_s2d_plan(escort_plan *p, cudaStream_t stream) {
+  const escort_geom &g = p->g;
+  if (g.stride_h != 2 || g.stride_w != 2 || g.dilation_h != 1 || g.dilation_w != 1 || p->nnz == 0) return 0;
+  if (getenv("ESCORT_NO_S2D") || p->parent) return 0;
+  const int KH2 = (g.kernel_h - 1) / 2 + 1, KW2 = (g.kernel_w - 1) / 2 + 1;
+  escort_plan *q = new escort_plan();
+  memset(q, 0, sizeof(*q));
+  q->g = g;
+  q->g.channels = 4 * g.channels;
+  q->g.height = p->Ho + KH2 - 1;
+  q->g.width = p->Wo + KW2 - 1;
+  q->g.kernel_h = KH2;
+  q->g.kernel_w = KW2;
+  q->g.pad_h = q->g.pad_w = 0;
+  q->g.stride_h = q->g.stride_w = 1;
+  q->Ho = p->Ho;
+  q->Wo = p->Wo;
+  q->device = p->device;
+  q->generic_backward = p->generic_backward;  // its own backward-data sub-plan serves the layer's stride-2 backward data
+  q->tile_w_tried = 1;                          // (no W variant for the parity-plane kernel sizes)
+  q->mu = new std::mutex();
+  q->nnz = p->nnz;
+  q->variant = -1;
+  q->host_nz = new std::vector<Nz>();
+  q->host_nz->reserve(p->nnz);
+  std::vector<int> dense_idx;
+  dense_idx.reserve(p->nnz);
+  for (const Nz &z : *p->host_nz) {  // (same order as the layer's nonzeros: d_meta[j] is nonzero j of both)
+    Nz t = z;
+    t.ic = 4 * z.ic + 2 * (z.kh & 1) + (z.kw & 1);
+    t.kh = z.kh >> 1;
+    t.kw = z.kw >> 1;
+    q->host_nz->push_back(t);
+    dense_idx.push_back(z.dense_idx);
+  }
+  int rc = upload(&q->d_dense_idx, dense_idx, stream);
+  if (!rc) rc = tile_plan_build(q, -1, stream);
+  if (!rc) {
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) rc = cuda_fail(e, "cudaStreamSynchronize", __FILE__, __LINE__);
+  }
+  if (rc || (!q->tile && !q->tm)) {
+    escort_plan_destroy(q);
+    return rc;
+  }
+  q->parent = p;
+  p->s2d = q;
+  p->use_s2d = s2d_by_default(p);
+  return 0;
+}
+
 extern "C" long escort_plan_nnz(const escort_plan *p) { return p ? p->nnz : -1; }
 
 extern "C" const char *escort_plan_kernel_name(const escort_plan *p) {
   if (!p) return "null";
+  if (p->use_s2d && p->s2d) return escort_plan_kernel_name(p->s2d);  // (escort_plan_describe says "s2d: ...")
   if (p->tm) return tmem_kernel_name(p->tm);
   if (p->tile) return tile_kernel_name(p->tile);
   const size_t img_bytes = (size_t)p->g.channels * p->g.height * p->g.width * sizeof(float);
@@ -601,6 +708,13 @@ extern "C" int escort_plan_get_config(const escort_plan *p, int *variant_host, i
 
 extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_rank) {
   ESCORT_REQUIRE(p && layout_rank >= 0, "escort_plan_set_config: bad arguments");
+  if (variant == -2) {  // the space-to-depth path of a stride-2 layer (its sub-plan keeps its own configuration)
+    ESCORT_REQUIRE(p->s2d, "escort_plan_set_config: variant -2 (space-to-depth) needs a stride-2 layer");
+    p->use_s2d = 1;
+    p->variant = -2;
+    return 0;
+  }
+  p->use_s2d = variant == -1 ? s2d_by_default(p) : 0;  // an explicit variant means that kernel on the strided input
   p->layout_rank = layout_rank;
   if (p->tile) {
     tile_plan_free(p->tile);
@@ -616,7 +730,8 @@ extern "C" int escort_plan_set_config(escort_plan *p, int variant, int layout_ra
   if (rc) return rc;
   // a stream built after escort_refresh_values starts from the create-time snapshot (host_nz): re-gather the current
   // values from the layer plan's device copy
-  const escort_plan *root = p->parent ? p->parent : p;
+  const escort_plan *root = p;
+  while (root->parent) root = root->parent;  // (the backward-data plan of a space-to-depth sub-plan is two levels down)
   if (root->refreshed && root->d_meta && (p->tile || p->tm)) {
     rc = tile_regather(p, root->d_meta, 0);
     if (rc) return rc;
@@ -709,6 +824,7 @@ extern "C" int escort_plan_copy_tuning(escort_plan *dst, const escort_plan *src,
   ESCORT_REQUIRE(memcmp(&dst->g, &src->g, sizeof(escort_geom)) == 0, "escort_plan_copy_tuning: geometries differ");
   int rc = escort_plan_set_config(dst, src->variant, src->layout_rank);
   if (rc) return rc;
+  if (src->s2d && dst->s2d && (rc = escort_plan_set_config(dst->s2d, src->s2d->variant, src->s2d->layout_rank))) return rc;
   if (src->bwd) {
     if (!dst->bwd && !dst->bwd_tried) {
       rc = build_bwd_plan(dst, stream);
@@ -731,7 +847,44 @@ extern "C" int escort_plan_copy_tuning(escort_plan *dst, const escort_plan *src,
 extern "C" int escort_plan_autotune(escort_plan *p, int num, escort_stream_t stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   ESCORT_REQUIRE(p && num > 0, "escort_plan_autotune: bad arguments");
-  return autotune_one(p, num, stream);
+  int rc = autotune_one(p, num, stream);
+  if (rc || !p->s2d) return rc;
+  // stride 2: the best kernel on the strided input (just chosen) against the space-to-depth path with its own tuned sub-plan
+  const int direct_v = p->variant, direct_rank = p->layout_rank;
+  if ((rc = autotune_one(p->s2d, num, stream))) return rc;
+  const escort_geom &g = p->g;
+  float *x = nullptr, *y = nullptr;
+  ESCORT_CUDA(cudaMalloc((void **)&x, (size_t)num * g.channels * g.height * g.width * sizeof(float)));
+  cudaError_t e = cudaMalloc((void **)&y, (size_t)num * g.num_output * p->Ho * p->Wo * sizeof(float));
+  if (e != cudaSuccess) {
+    cudaFree(x);
+    return cuda_fail(e, "cudaMalloc(autotune scratch)", __FILE__, __LINE__);
+  }
+  cudaMemsetAsync(x, 0, (size_t)num * g.channels * g.height * g.width * sizeof(float), stream);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best[2] = {1e30f, 1e30f};
+  for (int mode = 0; mode < 2; ++mode) {
+    p->use_s2d = mode;
+    for (int it = 0; it < 3; ++it) {
+      cudaEventRecord(e0, stream);
+      const int frc = escort_sconv_forward(p, num, x, nullptr, 0, y, stream);
+      cudaEventRecord(e1, stream);
+      float ms = 1e30f;
+      if (cudaEventSynchronize(e1) == cudaSuccess && frc == 0) cudaEventElapsedTime(&ms, e0, e1);
+      if (it > 0 && ms < best[mode]) best[mode] = ms;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(x);
+  cudaFree(y);
+  cudaGetLastError();
+  p->use_s2d = best[1] < best[0] ? 1 : 0;
+  p->variant = p->use_s2d ? -2 : direct_v;
+  p->layout_rank = direct_rank;
+  return 0;
 }
 
 extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_stream_t stream_) {
@@ -746,6 +899,17 @@ extern "C" int escort_plan_autotune_backward(escort_plan *p, int num, escort_str
     int rc = autotune_one(p->bwd, num, stream);
     if (rc) return rc;
   }
+  if (p->s2d && !p->generic_backward) {  // stride 2: the backward-data plan of the space-to-depth sub-plan
+    escort_plan *q = p->s2d;
+    if (!q->bwd && !q->bwd_tried) {
+      int rc = build_bwd_plan(q, stream);
+      if (rc) return rc;
+    }
+    if (q->bwd) {
+      int rc = autotune_one(q->bwd, num, stream);
+      if (rc) return rc;
+    }
+  }
   if (p->generic_backward || getenv("ESCORT_BWDW_VARIANT")) return 0;
   return tile_bwdw_autotune(p, num, stream);  // and the backward-weight (W) variant
 }
@@ -756,6 +920,24 @@ extern "C" int escort_sconv_forward(escort_plan *p, int num, const float *bottom
   ESCORT_REQUIRE(p && num >= 0, "escort_sconv_forward: bad arguments");
   if (num == 0) return 0;  // empty batch: nothing to do (pointers may be null)
   ESCORT_REQUIRE(bottom && top, "escort_sconv_forward: null tensor");
+  if (p->use_s2d && p->s2d) {  // stride 2: parity planes of the padded input, then the stride-1 sub-plan
+    const escort_geom &q = p->s2d->g;
+    const size_t need = (size_t)num * q.channels * q.height * q.width;
+    {
+      std::lock_guard<std::mutex> lock(*p->mu);
+      if (need > p->s2d_elems) {  // first call / larger batch: (re)allocate the library-owned buffer (synchronises the device)
+        cudaFree(p->s2d_buf);
+        p->s2d_buf = nullptr;
+        p->s2d_elems = 0;
+        ESCORT_CUDA(cudaMalloc((void **)&p->s2d_buf, need * sizeof(float)));
+        p->s2d_elems = need;
+      }
+    }
+    s2d_pad_kernel<<<(unsigned)((need + 255) / 256), 256, 0, stream>>>((long)need, bottom, p->g.channels, p->g.height, p->g.width,
+                                                                     p->g.pad_h, p->g.pad_w, q.height, q.width, p->s2d_buf);
+    ESCORT_LAUNCH_CHECK();
+    return escort_sconv_forward(p->s2d, num, p->s2d_buf, bias, fuse_relu, top, stream_);
+  }
   if (p->tm && tmem_batch_fits(p, num)) return tmem_forward(p, num, bottom, bias, fuse_relu, top, stream);
   if (p->tile) {
     const int rc = tile_forward(p, num, bottom, bias, fuse_relu, top, stream);
@@ -797,6 +979,29 @@ extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *
   ESCORT_REQUIRE(p && num >= 0 && num <= 65535, "escort_sconv_backward_data: bad arguments");
   if (num == 0) return 0;
   ESCORT_REQUIRE(top_diff && bottom_diff, "escort_sconv_backward_data: null tensor");
+  if (p->s2d && !p->generic_backward) {
+    // stride 2: the gradient of the parity planes through the sub-plan's own backward-data plan (a stride-1 forward
+    // kernel over its transposed weights), then depth-to-space without the padding
+    escort_plan *q = p->s2d;
+    const size_t need = (size_t)num * q->g.channels * q->g.height * q->g.width;
+    {
+      std::lock_guard<std::mutex> lock(*p->mu);
+      if (need > p->s2d_elems) {
+        cudaFree(p->s2d_buf);
+        p->s2d_buf = nullptr;
+        p->s2d_elems = 0;
+        ESCORT_CUDA(cudaMalloc((void **)&p->s2d_buf, need * sizeof(float)));
+        p->s2d_elems = need;
+      }
+    }
+    int rc = escort_sconv_backward_data(q, num, top_diff, p->s2d_buf, stream_);
+    if (rc) return rc;
+    const long total = (long)num * p->g.channels * p->g.height * p->g.width;
+    d2s_unpad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(total, p->s2d_buf, p->g.channels, p->g.height, p->g.width,
+                                                                        p->g.pad_h, p->g.pad_w, q->g.height, q->g.width, bottom_diff);
+    ESCORT_LAUNCH_CHECK();
+    return 0;
+  }
   if (!p->bwd && !p->bwd_tried && !p->generic_backward) {
     std::lock_guard<std::mutex> lock(*p->mu);  // first use: one thread builds, the others find it built
     if (!p->bwd && !p->bwd_tried) {
@@ -810,6 +1015,7 @@ extern "C" int escort_sconv_backward_data(escort_plan *p, int num, const float *
     else if (p->bwd->tile) rc = tile_forward(p->bwd, num, top_diff, nullptr, 0, bottom_diff, stream);
     if (rc != ESCORT_ETRYGENERIC) return rc;
   }
+  ESCORT_REQUIRE(p->d_colptr, "escort_sconv_backward_data: this launch needs the generic kernel, which a sub-plan does not have");
   const escort_geom &g = p->g;
   dim3 grid(ceil_div(g.height * g.width, kGenThreads), g.channels, num);
   sconv_bwd_data_generic_kernel<<<grid, kGenThreads, 0, stream>>>(p->d_colptr, p->d_tmeta, top_diff, bottom_diff,
@@ -883,7 +1089,11 @@ extern "C" int escort_refresh_values(escort_plan *p, const float *weights_dense,
     int rc = tile_refresh(p->bwd, weights_dense, stream);
     if (rc) return rc;
   }
-  p->refreshed = 1;
+  if (p->s2d) {
+    int rc = tile_refresh(p->s2d, weights_dense, stream);  // (a backward plan of the sub-plan built later re-gathers from d_meta)
+    if (!rc && p->s2d->bwd) rc = tile_refresh(p->s2d->bwd, weights_dense, stream);
+    if (rc) return rc;
+  }
   p->refreshed = 1;
   if (p->tile || p->tm) return tile_refresh(p, weights_dense, stream);
   return 0;

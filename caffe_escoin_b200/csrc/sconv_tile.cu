@@ -1026,7 +1026,14 @@ static int describe_tile(const TilePlan *tp, char *buf, int buflen) {
 // " | bwd_data: <kernel + tiling>" and " | bwd_weight: <kernel + tiling>"
 extern "C" ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen) {
   if (!plan || !buf || buflen <= 0) return ESCORT_EINVAL;
-  int n = plan->tm ? tmem_describe(plan->tm, buf, buflen) : plan->tile ? describe_tile(plan->tile, buf, buflen) : snprintf(buf, buflen, "generic");
+  int n = 0;
+  if (plan->use_s2d && plan->s2d) {  // stride 2 through the space-to-depth sub-plan: "<kernel> ... (s2d)"
+    const escort_plan *q = plan->s2d;
+    n = q->tm ? tmem_describe(q->tm, buf, buflen) : q->tile ? describe_tile(q->tile, buf, buflen) : snprintf(buf, buflen, "generic");
+    if (n > 0 && n < buflen - 8) n += snprintf(buf + n, buflen - n, " (s2d)");
+  } else {
+    n = plan->tm ? tmem_describe(plan->tm, buf, buflen) : plan->tile ? describe_tile(plan->tile, buf, buflen) : snprintf(buf, buflen, "generic");
+  }
   if (plan->bwd && (plan->bwd->tile || plan->bwd->tm) && n > 0 && n < buflen - 16) {
     n += snprintf(buf + n, buflen - n, " | bwd_data: ");
     if (n < buflen) n += plan->bwd->tm ? tmem_describe(plan->bwd->tm, buf + n, buflen - n) : describe_tile(plan->bwd->tile, buf + n, buflen - n);

@@ -102,7 +102,11 @@ ESCORT_API long escort_plan_nnz(const escort_plan *plan);
 ESCORT_API const char *escort_plan_kernel_name(const escort_plan *plan);
 /* human-readable tiling summary of the selected forward kernel, written to buf (NUL terminated) */
 ESCORT_API int escort_plan_describe(const escort_plan *plan, char *buf, int buflen);
-/* tuning knob for tests/bench: force a forward variant (-1 auto, 0 generic, >0 tile-interpreter variants) */
+/* tuning knob for tests/bench: force a forward variant (-1 auto; 0 generic / small-map kernel; > 0 tile-interpreter and
+ * TMEM-window variants; -2, stride-2 layers only: the space-to-depth path -- a stride-1 plan over the four parity planes
+ * of the padded input, written by one extra pass into a buffer the plan owns (sized for the largest batch seen; a plan's
+ * forward calls must therefore not overlap on different streams).  Auto uses it where the measured sweep says it wins,
+ * escort_plan_autotune measures both paths) */
 ESCORT_API int escort_plan_set_variant(escort_plan *plan, int variant);
 
 /* tuning knob: variant as above plus which of the planner's tiling candidates to use (0 = its favourite) */

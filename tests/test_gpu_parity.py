@@ -194,6 +194,63 @@ def test_small_map_kernel_is_bit_identical_to_the_generic_kernel(capi, po, case,
     assert po.rel_l2(outs[False], y_or) < TOL
 
 
+S2D_CASES = [
+    # N, Cin, Cout, H, W, k, pad, group, sparsity, bias, relu   (stride 2)
+    (3, 12, 16, 14, 14, 3, 1, 1, 0.5, True, False),
+    (2, 16, 24, 15, 13, 3, 1, 2, 0.7, True, True),     # odd, non-square, groups
+    (2, 8, 12, 28, 28, 5, 2, 1, 0.8, False, False),    # 5x5: a 3x3 kernel over the parity planes
+    (2, 8, 8, 9, 9, 1, 0, 1, 0.4, True, False),        # 1x1 stride 2 (ResNet's down-sampling shape)
+    (2, 6, 10, 11, 11, 3, 0, 1, 0.6, True, True),      # no padding
+    (1, 128, 32, 56, 56, 3, 1, 1, 0.7, False, False),  # large enough for the parity-plane path to be the default
+]
+
+
+@pytest.mark.parametrize("case", S2D_CASES, ids=lambda c: "N%d_C%d_M%d_H%dx%d_k%d_p%d_g%d_sp%g" % c[:9])
+def test_stride2_through_space_to_depth(capi, po, case):
+    """A stride-2 layer runs by default as a stride-1 convolution over the parity planes of the padded input (core.cu
+    build_s2d_plan): against the oracle, after autotune (which may keep either path), after a refresh, and against the
+    kernels that read the strided input directly (explicit variant)."""
+    from caffe_escoin_b200 import workloads as wl
+    torch = _torch()
+    N, Cin, Cout, H, W, k, pad, grp, sp, has_bias, relu = case
+    rng = np.random.default_rng(hash(case[:9]) % (2 ** 31))
+    w = wl.prune_magnitude((rng.standard_normal((Cout, Cin // grp, k, k)) * 0.05).astype(np.float32), sp)
+    bias = (rng.standard_normal(Cout) * 0.1).astype(np.float32) if has_bias else None
+    x = rng.uniform(-1, 1, (N, Cin, H, W)).astype(np.float32)
+    g = po.Geom(N, Cin, H, W, Cout, k, 2, pad, 1, grp)
+    y_or = po.conv_forward(x, po.weight_align(w, g), g, bias, relu=relu)
+    geom = capi.make_geom(Cin, Cout, H, W, k, 2, pad, 1, grp)
+    wd, xd = torch.from_numpy(w).cuda(), torch.from_numpy(x).cuda()
+    bd = torch.from_numpy(bias).cuda() if has_bias else None
+    plan = capi.Plan(geom, capi.weight_align(wd, geom))
+    # default without a measurement: the parity-plane path only where the sweep says it wins (channels x height >= 128 x 56)
+    assert ("(s2d)" in plan.describe()) == ((Cin // grp) * H >= 128 * 56), plan.describe()
+    plan.set_config(-2, 0)                   # the space-to-depth path by its variant id
+    assert "(s2d)" in plan.describe(), plan.describe()
+    y = plan.forward(xd, bd, relu=relu)
+    assert po.rel_l2(y.cpu().numpy(), y_or) < TOL, plan.describe()
+    plan.set_variant(0)                      # the generic / small-map kernel on the strided input
+    assert "(s2d)" not in plan.describe()
+    assert po.rel_l2(plan.forward(xd, bd, relu=relu).cpu().numpy(), y_or) < TOL
+    plan.autotune(N)                         # measures both paths, keeps the faster
+    assert po.rel_l2(plan.forward(xd, bd, relu=relu).cpu().numpy(), y_or) < TOL, plan.describe()
+    v, rank = plan.get_config()
+    plan.set_config(-2, 0)                   # the space-to-depth path by its variant id (what a tune cache stores)
+    assert "(s2d)" in plan.describe()
+    w2 = (w * 1.5).astype(np.float32)        # a solver update: same mask, new values
+    plan.refresh_values(torch.from_numpy(w2).cuda())
+    y2_or = po.conv_forward(x, po.weight_align(w2, g), g, bias, relu=relu)
+    assert po.rel_l2(plan.forward(xd, bd, relu=relu).cpu().numpy(), y2_or) < TOL
+    y_small = plan.forward(xd[:1].contiguous(), bd, relu=relu)   # another batch size through the same buffer
+    assert po.rel_l2(y_small.cpu().numpy(), y2_or[:1]) < TOL
+    # backward data of the stride-2 layer: the parity-plane sub-plan's own backward-data plan + depth-to-space, with the
+    # refreshed weights (the sub-plan's backward plan is built after the refresh: it must gather the current values)
+    dy = rng.uniform(-1, 1, y_or.shape).astype(np.float32)
+    _, _, dx_or = po.conv_backward(x, dy, w2, g, mask_only=True, want_b=False)
+    dx = plan.backward_data(torch.from_numpy(dy).cuda())
+    assert po.rel_l2(dx.cpu().numpy(), dx_or) < TOL
+
+
 def test_forward_raw_and_stretched_plans_agree(capi, po):
     from caffe_escoin_b200 import workloads as wl
     spec = wl.ALEXNET[3]._replace(N=2, Cin=32, Cout=32)

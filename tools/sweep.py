@@ -2,7 +2,7 @@
 """BASELINE.json configs[4]: single-layer sweep, sparsity 50-95 % x C=M 64-512 x H=W 7-56 x stride 1/2 (3x3, pad 1, N=64):
 our direct sparse conv (default plan, no autotune) against the reference's own GPU direct sconv (oracle/_ref, a slice of
 the batch: it syncs the device after every launch), with the per-point roofline fraction.
-    python tools/sweep.py [--autotune] > gpurun_out/sweep.jsonl"""
+    python tools/sweep.py [--autotune] [--stride 1|2] > gpurun_out/sweep.jsonl"""
 import ctypes as C
 import json
 import os
@@ -42,7 +42,10 @@ def main():
         pass
     R = C.CDLL(po.ref_gpu_path()) if po.have_ref_gpu() else None
     print(json.dumps({"fp32_peak_tflops": peak, "hbm_gbs": hbm, "reference_gpu": R is not None}), flush=True)
+    only_stride = int(sys.argv[sys.argv.index("--stride") + 1]) if "--stride" in sys.argv else None
     for li, spec in enumerate(wl.sweep_specs(64)):
+        if only_stride is not None and spec.stride != only_stride:
+            continue
         d = wl.make_layer_data(spec, li)
         geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
         csr = capi.weight_align(torch.from_numpy(d["w"]).cuda(), geom)
@@ -56,7 +59,7 @@ def main():
         ms = time_cuda(lambda: plan.forward(x, b, top=y))
         t_roof = max(flops / (peak * 1e12), byts / (hbm * 1e9))
         rec = {"point": spec.name, "sparsity": spec.sparsity, "C": spec.Cin, "H": spec.H, "stride": spec.stride,
-               "nnz": int(plan.nnz), "kernel": plan.kernel_name, "ms": ms, "tflops": flops / ms / 1e9,
+               "nnz": int(plan.nnz), "kernel": plan.kernel_name, "s2d": "(s2d)" in plan.describe(), "ms": ms, "tflops": flops / ms / 1e9,
                "img_s": spec.N / ms * 1e3, "roofline_frac": t_roof / (ms * 1e-3),
                "bound": "fp32_fma" if flops / (peak * 1e12) >= byts / (hbm * 1e9) else "hbm"}
         if R is not None:

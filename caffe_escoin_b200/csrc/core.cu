@@ -520,15 +520,18 @@ extern "C" int escort_plan_destroy(escort_plan *p) {
   return 0;
 }
 
-// Backward data as a forward convolution (stride 1, no dilation): bottom_diff = conv(top_diff, W'), with
-// W'[ic][oc][kh'][kw'] = W[oc][ic][K-1-kh'][K-1-kw'] and pad' = K-1-pad, so the tile kernel (and its plan-time
+// Backward data as a forward convolution (stride 1): bottom_diff = conv(top_diff, W'), with
+// W'[ic][oc][kh'][kw'] = W[oc][ic][K-1-kh'][K-1-kw'], the same dilation and pad' = dilation*(K-1)-pad, so the tile kernel (and its plan-time
 // compiler) serves both directions.  The sub-plan indexes the ORIGINAL dense weight tensor, so escort_refresh_values
 // refreshes it from the same weights.  Returns 0 and leaves p->bwd null when the geometry does not qualify.
 static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
   p->bwd_tried = 1;
   const escort_geom &g = p->g;
-  if (g.stride_h != 1 || g.stride_w != 1 || g.dilation_h != 1 || g.dilation_w != 1) return 0;
-  if (g.kernel_h - 1 - g.pad_h < 0 || g.kernel_w - 1 - g.pad_w < 0 || p->nnz == 0) return 0;
+  if (g.stride_h != 1 || g.stride_w != 1) return 0;  // (stride 2 goes through the space-to-depth sub-plan's own backward plan)
+  // dilation carries over (same dilation, pad' = dilation * (K - 1) - pad): the TMEM-window kernels take it, the tile
+  // kernels do not -- tile_plan_build then leaves the sub-plan empty and the generic kernel stays
+  const int ph = g.dilation_h * (g.kernel_h - 1) - g.pad_h, pw = g.dilation_w * (g.kernel_w - 1) - g.pad_w;
+  if (ph < 0 || pw < 0 || p->nnz == 0) return 0;
   escort_plan *q = new escort_plan();
   memset(q, 0, sizeof(*q));
   q->g = g;
@@ -536,10 +539,10 @@ static int build_bwd_plan(escort_plan *p, cudaStream_t stream) {
   q->g.num_output = g.channels;
   q->g.height = p->Ho;
   q->g.width = p->Wo;
-  q->g.pad_h = g.kernel_h - 1 - g.pad_h;
-  q->g.pad_w = g.kernel_w - 1 - g.pad_w;
-  q->Ho = out_dim(q->g.height, q->g.pad_h, g.kernel_h, 1, 1);
-  q->Wo = out_dim(q->g.width, q->g.pad_w, g.kernel_w, 1, 1);
+  q->g.pad_h = ph;
+  q->g.pad_w = pw;
+  q->Ho = out_dim(q->g.height, q->g.pad_h, g.kernel_h, 1, g.dilation_h);
+  q->Wo = out_dim(q->g.width, q->g.pad_w, g.kernel_w, 1, g.dilation_w);
   if (q->Ho != g.height || q->Wo != g.width) {
     delete q;
     return 0;

@@ -58,4 +58,22 @@ for name, spec in [("no padding", wl.ConvSpec("lenet2", 4, 20, 50, 12, 5, 1, 0, 
     print("small map %-23s %-23s rel_l2 %.2e" % (name, plan.kernel_name, err), flush=True)
     bad += err > 1e-4
     del plan
+# stride 2 through the space-to-depth sub-plan: s2d_pad_kernel + stride-1 kernel, and backward data = the sub-plan's backward
+# plan + d2s_unpad_kernel
+spec = wl.ConvSpec("stride2", 3, 16, 24, 15, 3, 2, 1, 1, 0.7, True, False)
+d = wl.make_layer_data(spec, 3)
+g = po.Geom(spec.N, spec.Cin, spec.H, spec.H, spec.Cout, spec.k, spec.stride, spec.pad, 1, spec.group)
+ref = po.conv_forward(d["x"], po.weight_align(d["w"], g), g, d["bias"], relu=False)
+geom = capi.make_geom(spec.Cin, spec.Cout, spec.H, spec.H, spec.k, spec.stride, spec.pad, 1, spec.group)
+plan = capi.Plan(geom, capi.weight_align(cu(d["w"]), geom))
+plan.set_config(-2, 0)
+yy = plan.forward(cu(d["x"]), cu(d["bias"]), relu=False)
+dy = rng.uniform(-1, 1, ref.shape).astype(np.float32)
+dx = plan.backward_data(cu(dy))
+torch.cuda.synchronize()
+_, _, dx_o = po.conv_backward(d["x"], dy, d["w"], g, mask_only=True, want_w=False, want_b=False)
+e1, e2 = po.rel_l2(yy.cpu().numpy(), ref), po.rel_l2(dx.cpu().numpy(), dx_o)
+print("stride 2 space-to-depth           %-23s fwd rel_l2 %.2e  bwd-data rel_l2 %.2e" % (plan.describe().split(" ")[0] + " (s2d)", e1, e2), flush=True)
+bad += (e1 > 1e-4) + (e2 > 1e-4)
+del plan
 sys.exit(1 if bad else 0)

@@ -7,7 +7,7 @@
  *
  * Parity status: PINNED against the reference's own code compiled in place
  * (oracle/_ref/libescort_ref.so = /root/reference/include/caffe/util/sconv.hpp built by
- * oracle/Makefile; see tests/test_oracle_vs_ref.py and the committed fixtures in tests/golden/
+ * oracle/Makefile; see tests/test_oracle.py and the committed fixtures in tests/golden/
  * made by tools/make_golden.py).  The reference ships NO golden vectors / tests of its own for the
  * sparse path, so "the reference run here" is the pin.
  *

@@ -57,6 +57,26 @@ r02b)    # 1 GPU, end of round 2: everything above on the final code + the dense
     grep -E "rel_l2|ERROR SUMMARY|RACECHECK SUMMARY" $O/sanitizer_dense_$tool.log | tail -9
   done
   python tools/small_time.py > $O/small_maps.txt 2>&1
+  python tools/run_dense.py > $O/dense.txt 2>&1          # -> profiles/r02_dense_tcgen05.txt
+  python tools/run_block.py > $O/block.txt 2>&1          # -> profiles/r02_bottleneck_block.txt
+  python tools/run_stride2.py > $O/stride2.txt 2>&1      # -> profiles/r02_stride2_space_to_depth.txt
+  python tools/run_level1.py > $O/level1.txt 2>&1        # -> profiles/r02_level1_vs_level2.txt
+  ;;
+r02sweep) # 1 GPU, ~10 min: BASELINE configs[4] + every variant x layout against the generic kernel at full size
+  O=gpurun_out/r02b
+  mkdir -p $O
+  python tools/sweep.py --autotune > $O/sweep_autotuned.jsonl    # -> profiles/r02_sweep_config5_autotuned.jsonl (+ _summary.txt)
+  for a in "alexnet:0 256" "alexnet:1 256" "alexnet:2 256" "alexnet:3 256" "resnet50:0 64" "resnet50:3 256" "resnet50:7 256" \
+           "resnet50:13 256" "googlenet:0 128" "googlenet:1 128" "googlenet:2 128" "googlenet:6 128" "googlenet:12 128" "googlenet:17 128"; do
+    set -- $a; python tools/check_variants.py $1 $2
+  done > $O/check_variants.txt 2>&1                              # -> profiles/r02_check_variants_full_size.txt
+  ;;
+r02multi) # N GPUs (gpurun --gpus N): the default command under torchrun, as the driver's scaling run launches it
+  N=${2:-8}
+  O=gpurun_out/r02b
+  mkdir -p $O
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29543 \
+      bench.py --gpus $N --steps 10 --warmup 3 > $O/bench_alexnet_${N}gpu.json 2> $O/bench_alexnet_${N}gpu.err
   ;;
 sanitize) # 1 GPU, round 2: compute-sanitizer on a thin layer through one kernel of each family (generic, cp.async and
           # TMA tile variants, 51 TMEM producer/consumer, 59 TMEM self-fill) + the default backward kernels

@@ -278,6 +278,7 @@ def _make_layers(specs, args, capi, wl, torch, train, tune_cache):
             plan.copy_tuning(tuned[shape])
         elif spec.name in tune_cache and not train:
             plan.set_config(*tune_cache[spec.name])
+            tuned[shape] = plan   # (the other layers of this shape copy it instead of measuring again)
         else:
             plan.autotune(spec.N)
             if train:

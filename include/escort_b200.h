@@ -117,9 +117,11 @@ ESCORT_API int escort_plan_get_config(const escort_plan *plan, int *variant_host
  * fastest (plan-time selection, like cuDNN's find); synchronises `stream`.  Optional: without it the plan
  * uses a static default. */
 ESCORT_API int escort_plan_autotune(escort_plan *plan, int num, escort_stream_t stream);
-/* the same for the backward kernels: the backward-weight variant, and the backward-data kernel (stride-1 layers run it as a forward plan over the transposed, rotated
- * weights -- ConvolutionLayer::Backward_gpu's backward_gpu_gemm + col2im, src/caffe/layers/conv_layer.cu:64-68);
- * a no-op for geometries that use the generic backward kernel.  Training hosts call it once after WeightAlign. */
+/* the same for the backward kernels: the backward-weight variant, and the backward-data kernel (stride-1 layers, dilated
+ * or not, run it as a forward plan over the transposed, rotated weights; stride-2 layers through the backward plan of
+ * their space-to-depth sub-plan -- ConvolutionLayer::Backward_gpu's backward_gpu_gemm + col2im,
+ * src/caffe/layers/conv_layer.cu:64-68); a no-op for geometries that use the generic backward kernel.  Training hosts
+ * call it once after WeightAlign. */
 ESCORT_API int escort_plan_autotune_backward(escort_plan *plan, int num, escort_stream_t stream);
 /* apply another plan's tuning (same geometry) instead of measuring again */
 ESCORT_API int escort_plan_copy_tuning(escort_plan *dst, const escort_plan *src, escort_stream_t stream);

@@ -81,3 +81,25 @@ def test_generated_variants_are_consistent():
     src = open(os.path.join(ROOT, "caffe_escoin_b200", "csrc", "sconv_tile.cu")).read()
     for pref in set(re.findall(r'"(sconv_tile_\w+)"', src)):
         assert pref in names, pref
+
+
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: include/escort_b200.h compiles as C99 with -pedantic (what a cgo / ctypes-style binding or
+    Caffe's C++ both see), and a C program links against every entry it names."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "escort_b200.h"\n'
+                   'int main(void) { escort_geom g; (void)g; return escort_version() == 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + inc, "-fsyntax-only", str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    pkg = os.path.join(ROOT, "caffe_escoin_b200")
+    exe = tmp_path / "hdr"
+    r = subprocess.run(["gcc", "-std=c99", "-I" + inc, str(src), "-o", str(exe), "-L" + pkg, "-lescort_b200",
+                        "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + pkg, "-Wl,-rpath,/usr/local/cuda/lib64"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

@@ -11,8 +11,10 @@ Our arm prints ONE JSON line with
   value     images/s with the inputs resident in HBM (CUDA events, max over ranks),
   parity    per layer: relative L2 of the TIMED plan's outputs (the autotuned kernel, 8 images) against the reference's
             own CPU kernels (oracle/_ref); the run exits non-zero above 1e-4,
-  train     (default workload only) a short ResNet-50 forward + masked-backward step with the per-layer gradient
-            all-reduce issued through the library (escort_allreduce_grads on a real ncclComm_t, side stream),
+  train     (default workload only) a short ResNet-50 forward + masked-backward step with the gradient exchange issued
+            through the library (escort_allreduce_grads on a real ncclComm_t): both of the reference's modes -- per
+            layer on a side stream, or one flat all-reduce after the backward -- are measured and the faster is timed,
+  clocks    SM clock / throttle reasons polled through NVML every 5 ms during the timed region,
   e2e       images/s through the C-ABI with HOST buffers: pinned-host -> device copies of every layer input that
             comes from outside the path and device -> host copies of its outputs inside the timed region,
   roofline  the dominant kernel against max(nnz-FLOPs / FP32-FMA peak, compulsory bytes / HBM bandwidth),
